@@ -1,0 +1,72 @@
+"""ctypes binding of libgsr_b200.so — the C ABI declared in include/gsr_b200.h.
+
+There is no CPU fallback: if the CUDA library is missing this module raises, and every product
+entry point raises with it.
+"""
+import ctypes
+import os
+
+from . import _build
+
+_c = ctypes
+_vp, _i, _f, _i64, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64, _c.c_size_t
+
+# name -> (restype, argtypes); order and meaning exactly as include/gsr_b200.h
+PROTOTYPES = {
+    "gsr_abi_version": (_i, []),
+    "gsr_supported_channels": (_i, [_i]),
+    "gsr_error_string": (_c.c_char_p, [_i]),
+    "gsr_geom_bytes": (_sz, [_i]),
+    "gsr_image_bytes": (_sz, [_i, _i]),
+    "gsr_binning_bytes": (_sz, [_i, _i64, _i, _i]),
+    "gsr_forward_stage1": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
+                                _i, _i, _f, _f, _i, _vp, _vp, _sz, _vp, _vp]),
+    "gsr_forward_stage2": (_i, [_i, _i, _i64, _vp, _vp, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "gsr_backward": (_i, [_i, _i, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp,
+                          _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "gsr_visible_filter": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp]),
+    "gsr_position2d_filter": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
+    "gsr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "gsr_debug_export": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsr_launch_count": (_i64, [_i]),
+}
+
+_LIB = None
+
+
+class GsrError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """Load (never build implicitly on a GPU box: the .so travels with the repo)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise GsrError(
+            "libgsr_b200.so is missing (%s). Build it with `python -m gscream_b200._build` "
+            "(or __graft_entry__.build()); there is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gsr_abi_version() != 1:
+        raise GsrError("libgsr_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().gsr_error_string(code).decode()
+        if code == -4:
+            # the reference throws std::runtime_error here (rasterizer_impl.cu:246-249)
+            raise RuntimeError(msg)
+        raise GsrError("libgsr_b200 call failed (%d): %s" % (code, msg))

@@ -1,0 +1,322 @@
+// gsr_api.cu — the extern "C" boundary of libgsr_b200.so (declared in include/gsr_b200.h).
+//
+// Orchestrates the stages that CudaRasterizer::Rasterizer::{forward,backward,visible_filter,
+// position2D_filter,markVisible} orchestrate in the reference (CR/rasterizer_impl.cu:141-153,
+// 199-347, 350-406, 470-530, 536-643), on the caller's stream, with caller-owned scratch.
+#include "../../include/gsr_b200.h"
+#include "gsr_common.cuh"
+#include <atomic>
+
+namespace gsr {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// implemented in the other translation units
+struct PreArgs {
+	int P, C, D, M;
+	const float *means3D, *scales, *rotations, *opacities, *uncertainties, *cov3D_precomp, *shs, *colors_precomp;
+	const float *view, *proj, *campos;
+	float scale_modifier;
+	int W, H;
+	float tan_fovx, tan_fovy, focal_x, focal_y;
+	int gx, gy;
+	int prefiltered;
+	int *radii;
+	float *rec;
+	uint32_t *tiles_touched, *depth_key, *depth_val;
+	float *pos_x, *pos_y;
+	uint8_t *clamped;
+	float *rgb;
+};
+struct PreBwdArgs {
+	int P, C, D, M;
+	const float *means3D, *scales, *rotations, *cov3D_precomp, *shs;
+	const float *view, *proj, *campos;
+	const uint8_t *clamped;
+	float scale_modifier;
+	int W, H;
+	float tan_fovx, tan_fovy, h_x, h_y;
+	const int *radii;
+	const float *gacc;
+	float *dL_dmeans2D, *dL_dopacity, *dL_duncertainty, *dL_dcolors;
+	float *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drotations;
+	int accumulate;
+};
+cudaError_t launch_preprocess(int mode, const PreArgs &a, cudaStream_t stream);
+cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t stream);
+cudaError_t launch_preprocess_backward(const PreBwdArgs &a, cudaStream_t stream);
+cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStream_t stream);
+cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const GeomLayout &GL, char *binning,
+                          const BinningLayout &BL, char *image, const ImageLayout &IL, cudaStream_t stream);
+cudaError_t launch_blend_forward(int C, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+                                 const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
+                                 float *out_depth, float *out_unc, cudaStream_t stream);
+cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+                                  const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
+                                  const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
+                                  float *dL_dcolors, cudaStream_t stream);
+
+__global__ void export_records_kernel(int P, const float *__restrict__ rec, float *xy, float *depths, float *conic_opacity)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const float *r = rec + (size_t)i * GSR_REC_FLOATS;
+	if (xy) { xy[2 * i] = r[0]; xy[2 * i + 1] = r[1]; }
+	if (depths) depths[i] = r[6];
+	if (conic_opacity) {
+		conic_opacity[4 * i + 0] = r[2];
+		conic_opacity[4 * i + 1] = r[3];
+		conic_opacity[4 * i + 2] = r[4];
+		conic_opacity[4 * i + 3] = r[5];
+	}
+}
+
+static bool channels_ok(int C) { return C == 3 || C == 32; }
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+} // namespace gsr
+
+using namespace gsr;
+
+#define GSR_CUDA(x)                                  \
+	do {                                             \
+		cudaError_t _e = (x);                        \
+		if (_e != cudaSuccess) return (int)_e;       \
+	} while (0)
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+int gsr_supported_channels(int channels) { return channels_ok(channels) ? 1 : 0; }
+
+const char *gsr_error_string(int code)
+{
+	switch (code) {
+	case 0: return "success";
+	case GSR_E_BADARG: return "gsr: bad argument (null pointer, negative size or misaligned buffer)";
+	case GSR_E_CHANNELS: return "gsr: unsupported channel count (supported: 3, 32)";
+	case GSR_E_WORKSPACE: return "gsr: scratch buffer too small";
+	case GSR_E_SH_CHANNELS: return "For non-RGB, provide precomputed Gaussian colors!";
+	default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gsr: unknown error";
+	}
+}
+
+size_t gsr_geom_bytes(int P) { return geom_layout(P).total; }
+size_t gsr_image_bytes(int width, int height) { return image_layout(width, height).total; }
+size_t gsr_binning_bytes(int P, int64_t num_rendered, int width, int height) { return binning_layout(P, num_rendered, width, height).total; }
+
+int64_t gsr_launch_count(int reset)
+{
+	return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int gsr_forward_stage1(int P, int C, int sh_degree, int M, const float *means3D, const float *shs, const float *colors_precomp,
+                       const float *opacities, const float *uncertainties, const float *scales, float scale_modifier,
+                       const float *rotations, const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                       const float *campos, int width, int height, float tan_fovx, float tan_fovy, int prefiltered, int *radii,
+                       void *geom_buffer, size_t geom_bytes, int64_t *num_rendered_host, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (P < 0 || width <= 0 || height <= 0 || !num_rendered_host) return GSR_E_BADARG;
+	*num_rendered_host = 0;
+	if (P == 0) return 0; // rasterize_points.cu:85
+	if (!means3D || !opacities || !uncertainties || !viewmatrix || !projmatrix || !radii || !geom_buffer) return GSR_E_BADARG;
+	if (!cov3D_precomp && (!scales || !rotations)) return GSR_E_BADARG;
+	if (!colors_precomp && !shs) return GSR_E_BADARG;
+	if (!colors_precomp && C != 3) return GSR_E_SH_CHANNELS; // CR/rasterizer_impl.cu:246-249
+	if (!colors_precomp && !campos) return GSR_E_BADARG;
+	if (!channels_ok(C)) return GSR_E_CHANNELS;
+	if (rotations && !aligned16(rotations)) return GSR_E_BADARG;
+	const GeomLayout L = geom_layout(P);
+	if (geom_bytes < L.total || !aligned16(geom_buffer)) return GSR_E_WORKSPACE;
+	char *geom = (char *)geom_buffer;
+
+	PreArgs a{};
+	a.P = P; a.C = C; a.D = sh_degree; a.M = M;
+	a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities; a.uncertainties = uncertainties;
+	a.cov3D_precomp = cov3D_precomp; a.shs = shs; a.colors_precomp = colors_precomp;
+	a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
+	a.scale_modifier = scale_modifier;
+	a.W = width; a.H = height;
+	a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+	a.focal_y = height / (2.0f * tan_fovy); // CR/rasterizer_impl.cu:226-227
+	a.focal_x = width / (2.0f * tan_fovx);
+	a.gx = (width + GSR_BLOCK_X - 1) / GSR_BLOCK_X;
+	a.gy = (height + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
+	a.prefiltered = prefiltered;
+	a.radii = radii;
+	a.rec = (float *)(geom + L.rec);
+	a.tiles_touched = (uint32_t *)(geom + L.tiles_touched);
+	a.depth_key = (uint32_t *)(geom + L.depth_key[0]);
+	a.depth_val = (uint32_t *)(geom + L.depth_val[0]);
+	a.clamped = (uint8_t *)(geom + L.clamped);
+	a.rgb = (float *)(geom + L.rgb);
+	GSR_CUDA(launch_preprocess(0, a, stream));
+	GSR_CUDA(depth_order_and_scan(P, geom, L, stream));
+	// R = offsets[P-1]: 4 bytes into the low half of the (pre-zeroed, little-endian) int64
+	GSR_CUDA(cudaMemcpyAsync(num_rendered_host, geom + L.offsets + (size_t)(P - 1) * 4, 4, cudaMemcpyDeviceToHost, stream));
+	return 0;
+}
+
+int gsr_forward_stage2(int P, int C, int64_t num_rendered, const float *colors_precomp, const float *background, int width, int height,
+                       void *geom_buffer, size_t geom_bytes, void *binning_buffer, size_t binning_bytes, void *image_buffer,
+                       size_t image_bytes, float *out_color, float *out_depth, float *out_uncertainty, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return GSR_E_BADARG;
+	if (P == 0) return 0;
+	if (!channels_ok(C)) return GSR_E_CHANNELS;
+	if (!background || !geom_buffer || !binning_buffer || !image_buffer || !out_color || !out_depth || !out_uncertainty) return GSR_E_BADARG;
+	if (C > 3 && (!colors_precomp || !aligned16(colors_precomp))) return GSR_E_BADARG;
+	const GeomLayout GL = geom_layout(P);
+	const ImageLayout IL = image_layout(width, height);
+	const BinningLayout BL = binning_layout(P, num_rendered, width, height);
+	if (geom_bytes < GL.total || image_bytes < IL.total || binning_bytes < BL.total) return GSR_E_WORKSPACE;
+	if (!aligned16(geom_buffer) || !aligned16(binning_buffer) || !aligned16(image_buffer)) return GSR_E_WORKSPACE;
+	char *geom = (char *)geom_buffer, *binning = (char *)binning_buffer, *image = (char *)image_buffer;
+
+	GSR_CUDA(bin_instances(P, num_rendered, width, height, geom, GL, binning, BL, image, IL, stream));
+	GSR_CUDA(launch_blend_forward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[1]),
+	                              (const float *)(geom + GL.rec), colors_precomp, background, (float *)(image + IL.final_T),
+	                              (uint32_t *)(image + IL.n_contrib), out_color, out_depth, out_uncertainty, stream));
+	return 0;
+}
+
+int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const float *background, int width, int height,
+                 const float *means3D, const float *shs, const float *colors_precomp, const float *scales, float scale_modifier,
+                 const float *rotations, const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                 const float *campos, float tan_fovx, float tan_fovy, const int *radii, void *geom_buffer, size_t geom_bytes,
+                 void *binning_buffer, size_t binning_bytes, void *image_buffer, size_t image_bytes, const float *dL_dout_color,
+                 const float *dL_dout_depth, const float *dL_dout_uncertainty, float *dL_dmeans2D, float *dL_dcolors,
+                 float *dL_dopacity, float *dL_duncertainty, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
+                 float *dL_dscales, float *dL_drotations, int accumulate, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return GSR_E_BADARG;
+	if (P == 0) return 0; // rasterize_points.cu:172
+	if (!channels_ok(C)) return GSR_E_CHANNELS;
+	if (!background || !means3D || !viewmatrix || !projmatrix || !radii || !geom_buffer || !binning_buffer || !image_buffer) return GSR_E_BADARG;
+	if (!dL_dout_color || !dL_dout_depth || !dL_dout_uncertainty) return GSR_E_BADARG;
+	if (!dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_duncertainty || !dL_dmeans3D) return GSR_E_BADARG;
+	if (!cov3D_precomp && (!scales || !rotations)) return GSR_E_BADARG;
+	if (C > 3 && (!colors_precomp || !aligned16(colors_precomp))) return GSR_E_BADARG;
+	if (rotations && !aligned16(rotations)) return GSR_E_BADARG;
+	if (shs && (!campos || !dL_dsh)) return GSR_E_BADARG;
+	const GeomLayout GL = geom_layout(P);
+	const ImageLayout IL = image_layout(width, height);
+	const BinningLayout BL = binning_layout(P, num_rendered, width, height);
+	if (geom_bytes < GL.total || image_bytes < IL.total || binning_bytes < BL.total) return GSR_E_WORKSPACE;
+	char *geom = (char *)geom_buffer, *binning = (char *)binning_buffer, *image = (char *)image_buffer;
+
+	float *gacc = (float *)(geom + GL.gacc);
+	GSR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 32, stream));
+	// colour gradients: accumulated straight into the caller's tensor by the blend backward.  With SH input
+	// they are an intermediate that the per-Gaussian kernel consumes, so they always start from zero.
+	if (!accumulate || shs) GSR_CUDA(cudaMemsetAsync(dL_dcolors, 0, (size_t)P * C * sizeof(float), stream));
+	count_launch(2);
+	if (num_rendered > 0) {
+		GSR_CUDA(launch_blend_backward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[1]),
+		                               (const float *)(geom + GL.rec), colors_precomp, background, (const float *)(image + IL.final_T),
+		                               (const uint32_t *)(image + IL.n_contrib), dL_dout_color, dL_dout_depth, dL_dout_uncertainty, gacc,
+		                               dL_dcolors, stream));
+	}
+	PreBwdArgs a{};
+	a.P = P; a.C = C; a.D = sh_degree; a.M = M;
+	a.means3D = means3D; a.scales = cov3D_precomp ? nullptr : scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp; a.shs = shs;
+	a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
+	a.clamped = (const uint8_t *)(geom + GL.clamped);
+	a.scale_modifier = scale_modifier;
+	a.W = width; a.H = height;
+	a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+	a.h_y = height / (2.0f * tan_fovy); // CR/rasterizer_impl.cu:580-581
+	a.h_x = width / (2.0f * tan_fovx);
+	a.radii = radii;
+	a.gacc = gacc;
+	a.dL_dmeans2D = dL_dmeans2D; a.dL_dopacity = dL_dopacity; a.dL_duncertainty = dL_duncertainty; a.dL_dcolors = dL_dcolors;
+	a.dL_dmeans3D = dL_dmeans3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drotations = dL_drotations;
+	a.accumulate = accumulate;
+	GSR_CUDA(launch_preprocess_backward(a, stream));
+	return 0;
+}
+
+static int run_filter(int mode, int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+                      const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, int width, int height,
+                      float tan_fovx, float tan_fovy, int prefiltered, int *radii, float *px, float *py, cudaStream_t stream)
+{
+	if (P < 0 || width <= 0 || height <= 0) return GSR_E_BADARG;
+	if (P == 0) return 0;
+	if (!means3D || !viewmatrix || !projmatrix || !radii) return GSR_E_BADARG;
+	if (!cov3D_precomp && (!scales || !rotations)) return GSR_E_BADARG;
+	if (rotations && !aligned16(rotations)) return GSR_E_BADARG;
+	if (mode == 2 && (!px || !py)) return GSR_E_BADARG;
+	PreArgs a{};
+	a.P = P; a.C = 3;
+	a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+	a.view = viewmatrix; a.proj = projmatrix;
+	a.scale_modifier = scale_modifier;
+	a.W = width; a.H = height;
+	a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+	a.focal_y = height / (2.0f * tan_fovy);
+	a.focal_x = width / (2.0f * tan_fovx);
+	a.gx = (width + GSR_BLOCK_X - 1) / GSR_BLOCK_X;
+	a.gy = (height + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
+	a.prefiltered = prefiltered;
+	a.radii = radii; a.pos_x = px; a.pos_y = py;
+	GSR_CUDA(launch_preprocess(mode, a, stream));
+	return 0;
+}
+
+int gsr_visible_filter(int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+                       const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, int width, int height,
+                       float tan_fovx, float tan_fovy, int prefiltered, int *radii, gsr_stream_t stream)
+{
+	return run_filter(1, P, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, width, height, tan_fovx,
+	                  tan_fovy, prefiltered, radii, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gsr_position2d_filter(int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+                          const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, int width, int height,
+                          float tan_fovx, float tan_fovy, int prefiltered, int *radii, float *position2D_x, float *position2D_y,
+                          gsr_stream_t stream)
+{
+	return run_filter(2, P, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, width, height, tan_fovx,
+	                  tan_fovy, prefiltered, radii, position2D_x, position2D_y, (cudaStream_t)stream);
+}
+
+int gsr_mark_visible(int P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present, gsr_stream_t stream)
+{
+	(void)projmatrix; // the reference's in_frustum computes p_proj but only tests view-space z (CR/auxiliary.h:154)
+	if (P < 0) return GSR_E_BADARG;
+	if (P == 0) return 0;
+	if (!means3D || !viewmatrix || !present) return GSR_E_BADARG;
+	GSR_CUDA(launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream));
+	return 0;
+}
+
+int gsr_debug_export(int P, int64_t num_rendered, int width, int height, const void *geom_buffer, const void *binning_buffer,
+                     const void *image_buffer, float *xy, float *depths, float *conic_opacity, uint32_t *tiles_touched,
+                     uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (P <= 0 || width <= 0 || height <= 0) return GSR_E_BADARG;
+	const GeomLayout GL = geom_layout(P);
+	const ImageLayout IL = image_layout(width, height);
+	const BinningLayout BL = binning_layout(P, num_rendered, width, height);
+	const char *geom = (const char *)geom_buffer, *binning = (const char *)binning_buffer, *image = (const char *)image_buffer;
+	const size_t N = (size_t)width * height;
+	const size_t tiles = (size_t)((width + GSR_BLOCK_X - 1) / GSR_BLOCK_X) * ((height + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y);
+	if (geom && (xy || depths || conic_opacity)) {
+		export_records_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, (const float *)(geom + GL.rec), xy, depths, conic_opacity);
+		GSR_CUDA(cudaGetLastError());
+	}
+	if (geom && tiles_touched) GSR_CUDA(cudaMemcpyAsync(tiles_touched, geom + GL.tiles_touched, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream));
+	if (binning && point_list && num_rendered > 0)
+		GSR_CUDA(cudaMemcpyAsync(point_list, binning + BL.val[1], (size_t)num_rendered * 4, cudaMemcpyDeviceToDevice, stream));
+	if (image && ranges) GSR_CUDA(cudaMemcpyAsync(ranges, image + IL.ranges, tiles * 8, cudaMemcpyDeviceToDevice, stream));
+	if (image && final_T) GSR_CUDA(cudaMemcpyAsync(final_T, image + IL.final_T, N * 4, cudaMemcpyDeviceToDevice, stream));
+	if (image && n_contrib) GSR_CUDA(cudaMemcpyAsync(n_contrib, image + IL.n_contrib, N * 4, cudaMemcpyDeviceToDevice, stream));
+	return 0;
+}
+
+} // extern "C"

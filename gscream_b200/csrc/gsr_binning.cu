@@ -1,0 +1,206 @@
+// gsr_binning.cu — tile binning: depth ordering, instance emission, per-tile stable bucketing, ranges.
+//
+// Replaces CR/rasterizer_impl.cu:283-324 of the reference (cub InclusiveSum over tiles_touched,
+// duplicateWithKeys :70-111, a 6-pass 64-bit cub::DeviceRadixSort over (tile<<32 | depth) keys
+// :309-314, identifyTileRanges :116-138) with a two-level scheme that produces the SAME point_list
+// and ranges bit for bit while moving ~4x fewer bytes:
+//
+//   1. sort the P Gaussians once by their 32-bit depth key (stable; culled ones carry 0xFFFFFFFF and
+//      end up last).  Ties keep ascending Gaussian index — exactly the tie-break the reference gets
+//      from emitting in index order and sorting stably.
+//   2. scan tiles_touched in that depth order, emit (tile id, Gaussian id) instances in depth order,
+//   3. stable radix sort of the R instances by tile id only (ceil(log2(tiles)) bits, 2 digit passes at
+//      1080p instead of 6), which leaves every tile's slab already depth-sorted,
+//   4. ranges from the sorted tile ids.
+//
+// Equivalence: the reference orders instances by (tile, depth bits) with ties broken by emission
+// order = Gaussian index (a Gaussian emits each tile at most once).  Step 1+3 yield (tile, depth bits,
+// Gaussian index) as well.  Depth keys are positive floats (z > 0.2), so their bit patterns order like
+// the values (CR/rasterizer_impl.cu:102-106).
+//
+// The radix-sort / scan primitives are CUB's for now (stop-gap, as allowed by SURVEY.md section 7);
+// everything around them is hand-written.
+#include "gsr_common.cuh"
+#include <cub/cub.cuh>
+
+namespace gsr {
+
+// -------- scratch layouts ---------------------------------------------------------------------
+static size_t sort_temp_bytes(int64_t n)
+{
+	// Out-of-place radix sort: CUB needs an alternate key and value array plus histograms / look-back
+	// state.  The query needs a CUDA device; the closed-form bound keeps the layout well defined (and
+	// identical) where there is none, and CUB re-checks the size it is given at sort time.
+	const size_t nn = (size_t)std::max<int64_t>(n, 1);
+	size_t bytes = 0;
+	cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+	                                                (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)nn);
+	if (e != cudaSuccess) { bytes = 0; (void)cudaGetLastError(); }
+	return std::max(bytes, 8 * nn + (size_t(1) << 22));
+}
+struct GatherTiles { // tiles_touched gathered through the depth order, fed to the scan as an input iterator
+	const uint32_t *tiles_touched;
+	const uint32_t *order;
+	__device__ __forceinline__ uint32_t operator()(int i) const { return tiles_touched[order[i]]; }
+};
+using GatherIter = cub::TransformInputIterator<uint32_t, GatherTiles, cub::CountingInputIterator<int>>;
+static size_t scan_temp_bytes(int n)
+{
+	size_t bytes = 0;
+	GatherIter in(cub::CountingInputIterator<int>(0), GatherTiles{nullptr, nullptr});
+	cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, bytes, in, (uint32_t *)nullptr, std::max(n, 1));
+	if (e != cudaSuccess) { bytes = 0; (void)cudaGetLastError(); }
+	return std::max(bytes, (size_t(1) << 20));
+}
+
+GeomLayout geom_layout(int P)
+{
+	GeomLayout L;
+	size_t off = 0;
+	const size_t p = (size_t)std::max(P, 1);
+	auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+	L.rec = take(p * GSR_REC_BYTES);
+	L.tiles_touched = take(p * 4);
+	L.depth_key[0] = take(p * 4);
+	L.depth_key[1] = take(p * 4);
+	L.depth_val[0] = take(p * 4);
+	L.depth_val[1] = take(p * 4);
+	L.offsets = take(p * 4);
+	L.gacc = take(p * 32);
+	L.clamped = take(p * 3);
+	L.rgb = take(p * 12);
+	L.temp_bytes = std::max(sort_temp_bytes(P), scan_temp_bytes(P));
+	L.temp = take(L.temp_bytes);
+	L.total = off;
+	return L;
+}
+
+ImageLayout image_layout(int W, int H)
+{
+	ImageLayout L;
+	size_t off = 0;
+	const size_t n = (size_t)std::max(W, 1) * (size_t)std::max(H, 1);
+	const size_t tiles = (size_t)((W + GSR_BLOCK_X - 1) / GSR_BLOCK_X) * (size_t)((H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y);
+	auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+	L.final_T = take(n * 4);
+	L.n_contrib = take(n * 4);
+	L.ranges = take(std::max<size_t>(tiles, 1) * 8);
+	L.total = off;
+	return L;
+}
+
+BinningLayout binning_layout(int P, int64_t R, int W, int H)
+{
+	(void)P; (void)W; (void)H;
+	BinningLayout L;
+	size_t off = 0;
+	const size_t r = (size_t)std::max<int64_t>(R, 1);
+	auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+	L.key[0] = take(r * 4);
+	L.key[1] = take(r * 4);
+	L.val[0] = take(r * 4);
+	L.val[1] = take(r * 4);
+	L.temp_bytes = sort_temp_bytes(R);
+	L.temp = take(L.temp_bytes);
+	L.total = off;
+	return L;
+}
+
+// -------- kernels -----------------------------------------------------------------------------
+// Instance emission in depth order (the reference's duplicateWithKeys runs in index order and writes
+// 64-bit keys; here the depth is already encoded in the position, so the key is just the tile id).
+__global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t *__restrict__ order,
+                                                             const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ tiles_touched,
+                                                             const float *__restrict__ rec, int gx, int gy,
+                                                             uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const uint32_t g = order[i];
+	const uint32_t tt = tiles_touched[g];
+	if (tt == 0) return;
+	uint32_t off = offsets[i] - tt;
+	const float2 xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
+	const int radius = (int)rec[(size_t)g * GSR_REC_FLOATS + 13];
+	int x0, y0, x1, y1;
+	get_rect(xy.x, xy.y, radius, gx, gy, x0, y0, x1, y1); // same rect as the forward (CR/rasterizer_impl.cu:92)
+	for (int y = y0; y < y1; y++)
+		for (int x = x0; x < x1; x++) {
+			keys[off] = (uint32_t)(y * gx + x);
+			vals[off] = g;
+			off++;
+		}
+}
+
+// identifyTileRanges, CR/rasterizer_impl.cu:116-138, on 32-bit tile ids.
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint32_t *__restrict__ keys, uint2 *__restrict__ ranges)
+{
+	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= L) return;
+	const uint32_t cur = keys[idx];
+	if (idx == 0)
+		ranges[cur].x = 0;
+	else {
+		const uint32_t prev = keys[idx - 1];
+		if (cur != prev) {
+			ranges[prev].y = (uint32_t)idx;
+			ranges[cur].x = (uint32_t)idx;
+		}
+	}
+	if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+}
+
+// -------- host orchestration --------------------------------------------------------------------
+// Stage-1 tail: depth order (always lands in depth_val[1]) + scan of tiles_touched in that order.
+// offsets[P-1] is then R (num_rendered).
+cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStream_t stream)
+{
+	if (P <= 0) return cudaSuccess;
+	size_t temp = L.temp_bytes;
+	cudaError_t e = cub::DeviceRadixSort::SortPairs(geom + L.temp, temp, (const uint32_t *)(geom + L.depth_key[0]),
+	                                                (uint32_t *)(geom + L.depth_key[1]), (const uint32_t *)(geom + L.depth_val[0]),
+	                                                (uint32_t *)(geom + L.depth_val[1]), P, 0, 32, stream);
+	if (e != cudaSuccess) return e;
+	count_launch(5);
+	const uint32_t *order = (const uint32_t *)(geom + L.depth_val[1]);
+	GatherTiles op{(const uint32_t *)(geom + L.tiles_touched), order};
+	GatherIter in(cub::CountingInputIterator<int>(0), op);
+	temp = L.temp_bytes;
+	e = cub::DeviceScan::InclusiveSum(geom + L.temp, temp, in, (uint32_t *)(geom + L.offsets), P, stream);
+	if (e != cudaSuccess) return e;
+	count_launch(2);
+	return cudaGetLastError();
+}
+
+// Stage-2 head: emission, per-tile bucketing (point_list always lands in val[1]), ranges.
+cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const GeomLayout &GL,
+                          char *binning, const BinningLayout &BL, char *image, const ImageLayout &IL, cudaStream_t stream)
+{
+	const int gx = (W + GSR_BLOCK_X - 1) / GSR_BLOCK_X, gy = (H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
+	const int tiles = gx * gy;
+	cudaError_t e = cudaMemsetAsync(image + IL.ranges, 0, (size_t)tiles * sizeof(uint2), stream); // CR/rasterizer_impl.cu:316
+	if (e != cudaSuccess) return e;
+	if (P <= 0 || R <= 0) return cudaSuccess;
+
+	const uint32_t *order = (const uint32_t *)(geom + GL.depth_val[1]);
+	emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order, (const uint32_t *)(geom + GL.offsets),
+	                                                         (const uint32_t *)(geom + GL.tiles_touched), (const float *)(geom + GL.rec),
+	                                                         gx, gy, (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
+	count_launch();
+	e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+
+	int bits = 1;
+	while ((1 << bits) < tiles) bits++;
+	size_t temp = BL.temp_bytes;
+	e = cub::DeviceRadixSort::SortPairs(binning + BL.temp, temp, (const uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.key[1]),
+	                                    (const uint32_t *)(binning + BL.val[0]), (uint32_t *)(binning + BL.val[1]), (int)R, 0, bits, stream);
+	if (e != cudaSuccess) return e;
+	count_launch(1 + (bits + 7) / 8);
+
+	tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, (const uint32_t *)(binning + BL.key[1]), (uint2 *)(image + IL.ranges));
+	count_launch();
+	return cudaGetLastError();
+}
+
+} // namespace gsr

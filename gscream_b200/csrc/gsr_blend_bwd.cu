@@ -1,0 +1,320 @@
+// gsr_blend_bwd.cu — backward tile blend: per-pixel -> per-Gaussian gradient scatter.
+//
+// Replaces renderCUDA<C> backward (CR/backward.cu:409-604 of W-Ted/GScream's
+// submodules/diff-gaussian-rasterization).  Same traversal (back to front from the last contributor,
+// T recovered by division, straight-through min(0.99,.), background term on colour channels only), but
+// restructured for the SM instead of translated:
+//
+//   * The reference keeps three per-thread arrays of C floats (accum_rec, last_color, dL_dpixel) and
+//     issues C+8 global float atomics per contributing (pixel, Gaussian) pair (179 registers and
+//     40 atomics per pair at C = 32).  Here the per-channel recurrence
+//         accum_rec[ch] <- last_alpha*last_color[ch] + (1-last_alpha)*accum_rec[ch]
+//         dL_dalpha     += (c[ch] - accum_rec[ch]) * dL_dpixel[ch]
+//     is collapsed, by linearity in ch, into ONE scalar recurrence on X = sum_ch accum_rec[ch]*g[ch]:
+//         X <- last_alpha*last_dot + (1-last_alpha)*X,   dL_dalpha = (dot - X) * T,   dot = f_j . g_p
+//     so a pixel needs only its gradient row g_p (C+2 registers) and three scalars.
+//   * Per-Gaussian sums over the warp's 32 pixels are formed on chip before touching global memory:
+//     the 8 geometric/scalar terms by a transpose-reduce butterfly (9 shuffles instead of 40), and, for
+//     C = 32, the C colour terms by switching roles — lane l owns channel l and holds the gradient
+//     COLUMN of its warp's 32 pixels in registers, the per-pixel weights alpha*T go through 128 B of
+//     shared memory, and the warp issues a single coalesced 128-B red.global.add per Gaussian.
+//     That is one RED instruction per (warp, Gaussian) where the reference issues 32 x C scalar atomics.
+//   * Same bulk-async slab staging and per-warp bounding-box compaction as the forward kernel, plus a
+//     tile-level skip of everything behind the deepest last contributor.
+//
+// Scalar terms are accumulated into gacc[P][8] = {dmean2D.x, dmean2D.y, dconic.x, dconic.y, dconic.w,
+// dopacity, ddepth, duncertainty}; colours into dL_dcolors[P][C].  Both must be zero (or hold the
+// running sum) on entry.
+#include "gsr_blend.cuh"
+
+namespace gsr {
+
+// Transpose-reduce: every lane contributes N values; afterwards v[0] on lane l is the warp-wide total
+// of value index vidx<N>(l).  N/2 + N/4 + ... + 1 exchanges, then plain xor-adds for the remaining strides.
+template <int N>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane)
+{
+	int s = 16;
+#pragma unroll
+	for (int n = N / 2; n >= 1; n >>= 1, s >>= 1) {
+		const bool upper = (lane & s) != 0;
+#pragma unroll
+		for (int i = 0; i < n; i++) {
+			const float send = upper ? v[i] : v[i + n];
+			const float keep = upper ? v[i + n] : v[i];
+			v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+		}
+	}
+#pragma unroll
+	for (; s >= 1; s >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], s);
+}
+template <int N>
+__device__ __forceinline__ int vidx(int lane)
+{
+	int idx = 0, s = 16;
+#pragma unroll
+	for (int n = N / 2; n >= 1; n >>= 1, s >>= 1)
+		if (lane & s) idx += n;
+	return idx;
+}
+template <int N>
+__device__ __forceinline__ bool vowner(int lane)
+{
+	// the lowest lane among those holding the same total
+	int rest = 32 / N - 1; // mask of the low bits not consumed by the exchange steps
+	return (lane & rest) == 0;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) blend_backward_kernel(
+    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int W, int H, int tiles_x,
+    const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
+    const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
+    const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dpixel_uncs,
+    float *__restrict__ gacc, float *__restrict__ dL_dcolors)
+{
+	using TR = BlendTraits<C>;
+	constexpr bool kLaneChannel = (C == 32); // colour sums by role switch; otherwise through the butterfly
+	constexpr int NV = kLaneChannel ? 8 : 16;
+	static_assert(kLaneChannel || C <= 8, "butterfly path carries at most 8 colour channels");
+
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	float *s_rec = reinterpret_cast<float *>(smem_raw);
+	float *s_feat = reinterpret_cast<float *>(smem_raw + (size_t)kBatch * GSR_REC_BYTES);
+	uint8_t *s_list = smem_raw + TR::kStageBytes;
+	uint8_t *s_mask = s_list + kWarpsPerTile * kBatch;
+	__shared__ __align__(8) uint64_t s_bar;
+	__shared__ __align__(16) float s_w[kWarpsPerTile][32];
+	__shared__ int s_red[kWarpsPerTile];
+	__shared__ uint32_t s_ids[kBatch];
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int tile = blockIdx.x;
+	const int tile_x0 = (tile % tiles_x) * GSR_BLOCK_X, tile_y0 = (tile / tiles_x) * GSR_BLOCK_Y;
+	int bx, by;
+	warp_block_origin(warp, bx, by);
+	const int px = tile_x0 + bx + (lane & 7), py = tile_y0 + by + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const float pixf_x = (float)px, pixf_y = (float)py;
+	const size_t plane = (size_t)H * W;
+	const size_t pix_id = (size_t)W * py + px;
+
+	const uint2 range = ranges[tile];
+	const float T_final = inside ? final_Ts[pix_id] : 0.f;
+	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+	// deepest last contributor of the warp / of the tile: nothing behind it can receive gradient
+	int warp_last = last_contributor;
+#pragma unroll
+	for (int s = 16; s >= 1; s >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, s));
+	if (lane == 0) s_red[warp] = warp_last;
+	if (tid == 0) {
+		mbar_init(&s_bar, 1);
+		mbar_fence_init();
+	}
+	__syncthreads();
+	int total = 0;
+#pragma unroll
+	for (int w = 0; w < kWarpsPerTile; w++) total = max(total, s_red[w]);
+	total = min(total, (int)(range.y - range.x));
+	if (total == 0) return;
+	const int rounds = (total + kBatch - 1) / kBatch;
+
+	// this pixel's upstream gradient row (colour channels, depth, uncertainty)
+	float g[C];
+	float gd = 0.f, gu = 0.f, bg_dot = 0.f;
+#pragma unroll
+	for (int ch = 0; ch < C; ch++) {
+		g[ch] = inside ? dL_dpixels[ch * plane + pix_id] : 0.f;
+		bg_dot += bg[ch] * g[ch];
+	}
+	if (inside) {
+		gd = dL_dpixel_depths[pix_id];
+		gu = dL_dpixel_uncs[pix_id];
+	}
+	// role switch (C == 32): lane l also holds channel l's gradient for the warp's 32 pixels
+	float gcol[kLaneChannel ? 32 : 1];
+	if (kLaneChannel) {
+		const float *src = dL_dpixels + (size_t)lane * plane;
+		const int x0 = tile_x0 + bx, y0 = tile_y0 + by;
+		const bool vec_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0) && (x0 + 8 <= W);
+#pragma unroll
+		for (int rr = 0; rr < 4; rr++) {
+			const int y = y0 + rr;
+			if (vec_ok && y < H) {
+				const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)W * y + x0);
+				const float4 a4 = __ldg(p4), b4 = __ldg(p4 + 1);
+				gcol[rr * 8 + 0] = a4.x; gcol[rr * 8 + 1] = a4.y; gcol[rr * 8 + 2] = a4.z; gcol[rr * 8 + 3] = a4.w;
+				gcol[rr * 8 + 4] = b4.x; gcol[rr * 8 + 5] = b4.y; gcol[rr * 8 + 6] = b4.z; gcol[rr * 8 + 7] = b4.w;
+			} else {
+#pragma unroll
+				for (int cc = 0; cc < 8; cc++) {
+					const int x = x0 + cc;
+					gcol[rr * 8 + cc] = (x < W && y < H) ? __ldg(src + (size_t)W * y + x) : 0.f;
+				}
+			}
+		}
+	}
+
+	float T = T_final;
+	float X = 0.f, last_alpha = 0.f, last_dot = 0.f;
+	const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
+
+	// staged slot t of round r holds list position total-1-(r*256+t): back to front (CR/backward.cu:500)
+	uint32_t next_id = (tid < total) ? point_list[range.x + (uint32_t)(total - 1 - tid)] : 0u;
+
+	for (int r = 0; r < rounds; r++) {
+		__syncthreads(); // previous batch fully consumed
+		const int base = r * kBatch;
+		const int count = min(kBatch, total - base);
+		if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)count * TR::kBytesPerGaussian);
+		uint32_t mask = 0;
+		if (tid < count) {
+			const uint32_t id = next_id;
+			s_ids[tid] = id;
+			const float *src = rec + (size_t)id * GSR_REC_FLOATS;
+			bulk_g2s(s_rec + tid * GSR_REC_FLOATS, src, GSR_REC_BYTES, &s_bar);
+			if (!TR::kFeatInRec) bulk_g2s(s_feat + tid * C, features + (size_t)id * C, C * 4, &s_bar);
+			const float2 cxy = __ldg(reinterpret_cast<const float2 *>(src));
+			const float2 ext = __ldg(reinterpret_cast<const float2 *>(src + 8));
+			mask = warp_overlap_mask(cxy.x, cxy.y, ext.x, ext.y, (float)tile_x0, (float)tile_y0);
+			// per-warp: positions at or behind the warp's deepest last contributor cannot contribute
+			const int pos = total - 1 - (base + tid);
+#pragma unroll
+			for (int w = 0; w < kWarpsPerTile; w++)
+				if (pos >= s_red[w]) mask &= ~(1u << w);
+		}
+		s_mask[tid] = (uint8_t)mask;
+		{
+			const int nb = base + kBatch + tid;
+			next_id = (nb < total) ? point_list[range.x + (uint32_t)(total - 1 - nb)] : 0u;
+		}
+		__syncthreads();
+		uint8_t *my_list = s_list + warp * kBatch;
+		const int n = build_warp_list(s_mask, my_list, warp, lane, count);
+		mbar_wait(&s_bar, (uint32_t)(r & 1));
+
+		for (int k = 0; k < n; k++) {
+			const int j = my_list[k];
+			const int pos = total - 1 - (base + j); // 0-based list position
+			const float4 r0 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS);     // x y a b
+			const float4 r1 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 4); // c o depth unc
+			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
+			const float power = -0.5f * (r0.z * d.x * d.x + r1.x * d.y * d.y) - r0.w * d.x * d.y;
+			const float G = exp(power);
+			const float alpha = min(0.99f, r1.y * G);
+			const bool valid = (pos < last_contributor) && !(power > 0.0f) && !(alpha < kAlphaMin);
+			if (!__any_sync(0xffffffffu, valid)) continue;
+
+			float v[NV];
+#pragma unroll
+			for (int i = 0; i < NV; i++) v[i] = 0.f;
+			float w = 0.f;
+			if (valid) {
+				T = T / (1.f - alpha);
+				w = alpha * T;
+				// dot = f_j . g_p over colour channels, depth and uncertainty
+				float dot = r1.z * gd + r1.w * gu;
+				if (TR::kFeatInRec) {
+					const float4 r2 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 8);
+					const float cb = s_rec[j * GSR_REC_FLOATS + 12];
+					if (C > 0) dot += r2.z * g[0];
+					if (C > 1) dot += r2.w * g[1 % C];
+					if (C > 2) dot += cb * g[2 % C];
+				} else {
+					const float4 *f4 = reinterpret_cast<const float4 *>(s_feat + j * C);
+#pragma unroll
+					for (int q = 0; q < C / 4; q++) {
+						const float4 f = f4[q];
+						dot += f.x * g[4 * q + 0];
+						dot += f.y * g[4 * q + 1];
+						dot += f.z * g[4 * q + 2];
+						dot += f.w * g[4 * q + 3];
+					}
+				}
+				X = last_alpha * last_dot + (1.f - last_alpha) * X;
+				last_dot = dot;
+				float dL_dalpha = (dot - X) * T;
+				last_alpha = alpha;
+				dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+
+				const float dL_dG = r1.y * dL_dalpha;
+				const float gdx = G * d.x, gdy = G * d.y;
+				const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+				const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+				v[0] = dL_dG * dG_ddelx * ddelx_dx;
+				v[1] = dL_dG * dG_ddely * ddely_dy;
+				v[2] = -0.5f * gdx * d.x * dL_dG;
+				v[3] = -0.5f * gdx * d.y * dL_dG;
+				v[4] = -0.5f * gdy * d.y * dL_dG;
+				v[5] = G * dL_dalpha;
+				v[6] = w * gd;
+				v[7] = w * gu;
+				if (!kLaneChannel) {
+#pragma unroll
+					for (int ch = 0; ch < C; ch++) v[8 + ch] = w * g[ch];
+				}
+			}
+			const uint32_t id = s_ids[j];
+
+			warp_transpose_reduce<NV>(v, lane);
+			if (vowner<NV>(lane)) {
+				const int q = vidx<NV>(lane);
+				if (q < 8) red_add(gacc + (size_t)id * 8 + q, v[0]);
+				else if (q < 8 + C) red_add(dL_dcolors + (size_t)id * C + (q - 8), v[0]);
+			}
+			if (kLaneChannel) {
+				s_w[warp][lane] = w;
+				__syncwarp();
+				float sum = 0.f;
+				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[warp]);
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const float4 ww = w4[q];
+					sum += ww.x * gcol[4 * q + 0];
+					sum += ww.y * gcol[4 * q + 1];
+					sum += ww.z * gcol[4 * q + 2];
+					sum += ww.w * gcol[4 * q + 3];
+				}
+				red_add(dL_dcolors + (size_t)id * C + lane, sum); // 32 lanes -> one coalesced 128-B RED
+				__syncwarp();
+			}
+		}
+	}
+}
+
+template <int C>
+static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, int W, int H, int tiles_x, const float *rec,
+                              const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
+                              const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
+                              float *dL_dcolors, cudaStream_t stream)
+{
+	using TR = BlendTraits<C>;
+	static bool configured = false;
+	if (!configured) {
+		cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR::kSmemBytes);
+		if (e != cudaSuccess) return e;
+		configured = true;
+	}
+	blend_backward_kernel<C><<<tiles, 256, TR::kSmemBytes, stream>>>(ranges, point_list, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
+	                                                                dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+                                  const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
+                                  const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
+                                  float *dL_dcolors, cudaStream_t stream)
+{
+	const int tiles_x = (W + GSR_BLOCK_X - 1) / GSR_BLOCK_X, tiles_y = (H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
+	const int tiles = tiles_x * tiles_y;
+	if (tiles <= 0) return cudaSuccess;
+	switch (C) {
+	case 3: return launch_bwd<3>(tiles, ranges, point_list, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+	case 32: return launch_bwd<32>(tiles, ranges, point_list, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+} // namespace gsr

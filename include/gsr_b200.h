@@ -1,0 +1,169 @@
+/*
+ * gsr_b200.h — C ABI of the B200-native differentiable Gaussian rasterizer.
+ *
+ * Drop-in boundary for W-Ted/GScream's `submodules/diff-gaussian-rasterization`
+ * (paths below are relative to that directory; CR/ = cuda_rasterizer/).  The
+ * reference binds its CUDA through five pybind11 functions (ext.cpp:16-20) over the
+ * C++ statics CudaRasterizer::Rasterizer::{forward,backward,visible_filter,
+ * position2D_filter,markVisible} (CR/rasterizer.h:20-133).  This header is what a
+ * replacement of those statics binds instead: plain device pointers, ints, floats and a
+ * cudaStream_t; no torch types, no exceptions, no allocation, no state between calls.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *  - all floating point is fp32, indices int32/uint32;
+ *  - viewmatrix / projmatrix are the 16 floats of the reference's (already transposed,
+ *    i.e. column-major) world_view_transform / full_proj_transform (scene/cameras.py:64-67);
+ *  - every function returns 0 on success, a cudaError_t value (> 0) if a launch failed, or a
+ *    negative GSR_E_* code for argument errors.  Errors are sticky-free: nothing is cached.
+ *  - `stream` is an opaque cudaStream_t (pass NULL for the legacy default stream);
+ *  - the three scratch buffers (geom / binning / image) are caller-allocated device byte
+ *    buffers sized by the gsr_*_bytes() queries and handed back unchanged to gsr_backward,
+ *    exactly like the reference's geomBuffer / binningBuffer / imgBuffer
+ *    (rasterize_points.cu:77-82, diff_gaussian_rasterization/__init__.py:105,122).
+ *    Their layout is private to this library.
+ */
+#ifndef GSR_B200_H_INCLUDED
+#define GSR_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GSR_API __attribute__((visibility("default")))
+#else
+#define GSR_API
+#endif
+
+#define GSR_E_BADARG      (-1) /* null pointer / negative size / misaligned buffer            */
+#define GSR_E_CHANNELS    (-2) /* unsupported channel count (see gsr_supported_channels)       */
+#define GSR_E_WORKSPACE   (-3) /* a scratch buffer is smaller than gsr_*_bytes() requires       */
+#define GSR_E_SH_CHANNELS (-4) /* SH input with C != 3 (CR/rasterizer_impl.cu:246-249)         */
+
+typedef void *gsr_stream_t;
+
+/* ABI / capability queries ------------------------------------------------------------- */
+GSR_API int gsr_abi_version(void);
+/* returns 1 if `channels` colour/feature channels can be blended (compiled instantiations) */
+GSR_API int gsr_supported_channels(int channels);
+/* human-readable text for a return code of this library (CUDA codes are forwarded to
+ * cudaGetErrorString) */
+GSR_API const char *gsr_error_string(int code);
+
+/* scratch sizing — replaces required<GeometryState/ImageState/BinningState>()
+ * (CR/rasterizer_impl.h:64-73, CR/rasterizer_impl.cu:155-195) */
+GSR_API size_t gsr_geom_bytes(int P);
+GSR_API size_t gsr_image_bytes(int width, int height);
+GSR_API size_t gsr_binning_bytes(int P, int64_t num_rendered, int width, int height);
+
+/*
+ * Forward, first half — replaces the part of Rasterizer::forward before the blocking
+ * cudaMemcpy of num_rendered (CR/rasterizer_impl.cu:199-287): per-Gaussian cull + EWA
+ * projection (preprocessCUDA, CR/forward.cu:157-267), depth ordering and the prefix sum of
+ * tiles_touched.
+ *   means3D[P,3] opacities[P] uncertainties[P] scales[P,3] rotations[P,4] (or cov3D_precomp[P,6])
+ *   shs[P,M,3] with sh_degree (or NULL/0 when colours are precomputed — the GScream case)
+ *   colors_precomp[P,C] (or NULL when shs is given; then C must be 3)
+ *   radii[P] (out, int32) — the reference's `radii` return value
+ *   num_rendered_host: PINNED host int64; written asynchronously on `stream`.  The caller
+ *   synchronises the stream (or an event) before reading it — this is the one host sync the
+ *   reference API forces (it returns num_rendered as a Python int).
+ */
+GSR_API int gsr_forward_stage1(
+    int P, int C, int sh_degree, int M,
+    const float *means3D, const float *shs, const float *colors_precomp,
+    const float *opacities, const float *uncertainties,
+    const float *scales, float scale_modifier, const float *rotations, const float *cov3D_precomp,
+    const float *viewmatrix, const float *projmatrix, const float *campos,
+    int width, int height, float tan_fovx, float tan_fovy, int prefiltered,
+    int *radii, void *geom_buffer, size_t geom_bytes,
+    int64_t *num_rendered_host, gsr_stream_t stream);
+
+/*
+ * Forward, second half — replaces CR/rasterizer_impl.cu:289-346: (tile, depth) instance
+ * emission (duplicateWithKeys :70-111), stable sort (:309-314), identifyTileRanges (:116-138)
+ * and the blend kernel renderCUDA (CR/forward.cu:441-568).
+ *   background[C]; out_color[C,H,W]; out_depth[1,H,W]; out_uncertainty[1,H,W]
+ */
+GSR_API int gsr_forward_stage2(
+    int P, int C, int64_t num_rendered,
+    const float *colors_precomp, const float *background,
+    int width, int height,
+    void *geom_buffer, size_t geom_bytes,
+    void *binning_buffer, size_t binning_bytes,
+    void *image_buffer, size_t image_bytes,
+    float *out_color, float *out_depth, float *out_uncertainty, gsr_stream_t stream);
+
+/*
+ * Backward — replaces Rasterizer::backward (CR/rasterizer_impl.cu:536-643): blend backward
+ * (renderCUDA, CR/backward.cu:409-604), computeCov2DCUDA (:144-274) and preprocessCUDA
+ * backward (:346-406).
+ * Gradient outputs (all fp32, shapes as rasterize_points.cu:160-170):
+ *   dL_dmeans2D[P,3] dL_dcolors[P,C] dL_dopacity[P] dL_duncertainty[P]  (accumulated with atomics)
+ *   dL_dmeans3D[P,3] dL_dcov3D[P,6] dL_dscales[P,3] dL_drotations[P,4] dL_dsh[P,M,3] (written)
+ * accumulate == 0: every output is overwritten (zero for culled Gaussians) — the reference's
+ *                  semantics with its torch::zeros allocation folded in;
+ * accumulate != 0: outputs are added to (gradient accumulation over views into one bucket;
+ *                  the caller zeroes the bucket once per step).
+ * dL_dcov3D / dL_dsh / dL_dscales / dL_drotations may be NULL when not wanted.
+ */
+GSR_API int gsr_backward(
+    int P, int C, int sh_degree, int M, int64_t num_rendered,
+    const float *background, int width, int height,
+    const float *means3D, const float *shs, const float *colors_precomp,
+    const float *scales, float scale_modifier, const float *rotations, const float *cov3D_precomp,
+    const float *viewmatrix, const float *projmatrix, const float *campos,
+    float tan_fovx, float tan_fovy, const int *radii,
+    void *geom_buffer, size_t geom_bytes,
+    void *binning_buffer, size_t binning_bytes,
+    void *image_buffer, size_t image_bytes,
+    const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_uncertainty,
+    float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_duncertainty,
+    float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
+    int accumulate, gsr_stream_t stream);
+
+/* Anchor pre-filters — replace Rasterizer::visible_filter / position2D_filter /
+ * markVisible (CR/rasterizer_impl.cu:350-406, 470-530, 141-153).  No scratch needed. */
+GSR_API int gsr_visible_filter(
+    int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+    const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+    int width, int height, float tan_fovx, float tan_fovy, int prefiltered,
+    int *radii, gsr_stream_t stream);
+
+GSR_API int gsr_position2d_filter(
+    int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+    const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+    int width, int height, float tan_fovx, float tan_fovy, int prefiltered,
+    int *radii, float *position2D_x, float *position2D_y, gsr_stream_t stream);
+
+GSR_API int gsr_mark_visible(
+    int P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+    uint8_t *present, gsr_stream_t stream);
+
+/*
+ * Introspection for parity tests (device -> device copies out of the private scratch layout).
+ * Any output pointer may be NULL.  Shapes: xy[P,2] depths[P] conic_opacity[P,4]
+ * tiles_touched[P] point_list[R] ranges[tiles,2] final_T[H*W] n_contrib[H*W].
+ * Entries of culled Gaussians (radii == 0) in xy/depths/conic_opacity are unspecified.
+ */
+GSR_API int gsr_debug_export(
+    int P, int64_t num_rendered, int width, int height,
+    const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
+    float *xy, float *depths, float *conic_opacity, uint32_t *tiles_touched,
+    uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib,
+    gsr_stream_t stream);
+
+/* Number of this library's kernel launches since the last call with reset != 0
+ * (bench.py reports it as `gpu_launches`). */
+GSR_API int64_t gsr_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H_INCLUDED */
