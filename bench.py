@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — forward+backward views/s of the Gaussian-rasterizer hot path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config2]
+
+One "step" = one view per GPU: forward (cull/project, bin, sort, blend) + backward (blend backward, per-Gaussian
+backward) of the named synthetic workload, gradients accumulated into one flat bucket, plus — at N > 1 — the single
+NCCL sum-allreduce of that bucket.  Default workload: BASELINE.json configs[2] ("config3": 1M Gaussians, 1920x1080,
+32 feature channels + depth + uncertainty), the configuration the metric is quoted on; it fits one GPU.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline` is for the dominant kernel (blend
+backward), `cpu_baseline` is the CPU oracle port timed on a bounded sample, `e2e` goes through the public
+GaussianRasterizer API with every input coming from pinned HOST memory inside the timed region.
+
+--impl reference times the reference's own CUDA build (oracle/_ref, compiled from /root/reference by
+oracle/build_ref.py; the reference ships no CPU rasterizer, so per BASELINE.json's north_star that build on the same
+GPU — with the host core count recorded — is the baseline arm) on the same config through its own Python API.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _timed(fn_step, steps, warmup, world, sampler=None):
+    """W untimed steps, then exactly K steps bracketed by barrier + synchronize; device time, max over ranks."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, clocks
+
+
+def algorithmic_bytes_blend_backward(C, W, H, R, V):
+    """B1 + 4 (K+6) V  with  B1 = 8 Tn + 28 R + 4 K R + 4 (K+2) N."""
+    K = C + 2
+    Tn = ((W + 15) // 16) * ((H + 15) // 16)
+    N = W * H
+    return 8 * Tn + 28 * R + 4 * K * R + 4 * (K + 2) * N + 4 * (K + 6) * V
+
+
+def cpu_baseline_port(cfg):
+    """CPU oracle (plain C, 1 thread) on a bounded sample of the workload: 1/16 of the Gaussians at 1/4 x 1/4 of the
+    image (same splat density and per-pixel depth complexity); reported as full-workload-equivalent views/s."""
+    from oracle.oracle import Oracle
+    from gscream_b200 import scenes
+    P, W, H, C = cfg["P"] // 16, cfg["W"] // 4, cfg["H"] // 4, cfg["C"]
+    s = scenes.make_scene(P, W, H, C, cfg["seed"])
+    cam = scenes.make_camera(W, H)
+    g = scenes.make_upstream_grads(C, W, H, cfg["seed"])
+    o = Oracle("f32")
+    a = dict(means3D=s["means3D"].numpy(), colors_precomp=s["colors"].numpy(), opacities=s["opacities"].numpy(),
+             uncertainties=s["uncertainties"].numpy(), scales=s["scales"].numpy(), rotations=s["rotations"].numpy(),
+             viewmatrix=cam["viewmatrix"].numpy(), projmatrix=cam["projmatrix"].numpy(), bg=s["bg"].numpy(), W=W, H=H,
+             tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"])
+    t0 = time.perf_counter()
+    f = o.forward(**a)
+    o.backward(f, means3D=a["means3D"], colors_precomp=a["colors_precomp"], scales=a["scales"], rotations=a["rotations"],
+               viewmatrix=a["viewmatrix"], projmatrix=a["projmatrix"], bg=a["bg"], W=W, H=H, tanfovx=a["tanfovx"], tanfovy=a["tanfovy"],
+               dL_dcolor=g[0].numpy(), dL_ddepth=g[1].numpy(), dL_dunc=g[2].numpy())
+    dt = time.perf_counter() - t0
+    return {"value": (1.0 / dt) / 16.0, "unit": "views/s", "cores": 1, "kind": "port",
+            "sample": "1/16 of the workload: %d Gaussians at %dx%d (same density), one fwd+bwd view in %.2f s on 1 thread; value = measured/16" % (P, W, H, dt)}
+
+
+def run_ours(args, cfg, rank, world, local):
+    import torch.distributed as dist
+    from gscream_b200 import _lib, scenes
+    from gscream_b200 import rasterizer as ours
+    from gscream_b200.dist import GradBucket, allreduce_bucket, render_views_into_bucket
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    P, W, H, C, seed = cfg["P"], cfg["W"], cfg["H"], cfg["C"], cfg["seed"]
+    scene_cpu = scenes.make_scene(P, W, H, C, seed)                       # identical bits on every rank
+    yaw = (rank - (world - 1) / 2.0) * 3.0                                # every rank renders its own view
+    cam_cpu = scenes.make_camera(W, H, yaw_deg=yaw)
+    grads_cpu = scenes.make_upstream_grads(C, W, H, seed + rank)
+    scene = {k: v.to(dev) for k, v in scene_cpu.items()}
+    cam = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in cam_cpu.items()}
+    ups = [tuple(g.to(dev) for g in grads_cpu)]
+    bucket = GradBucket(P, C, device=dev)
+    info = {}
+
+    def step():
+        bucket.zero_()
+        outs = render_views_into_bucket(scene, [cam], ups, bucket, keep_outputs=True)
+        info["R"] = outs[0][4]
+        info["radii"] = outs[0][3]
+        allreduce_bucket(bucket)
+
+    # ---- device-resident throughput (`value`) + per-stage device times ----
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    lib.gsr_profile_enable(1)
+    lib.gsr_launch_count(1)
+    ms, clocks = _timed(step, args.steps, 0, world, ClockSampler(local) if rank == 0 else None)
+    launches = int(lib.gsr_launch_count(0))
+    stage_ms = {}
+    buf = np.zeros(256, np.float32)
+    for sid, name in enumerate(("preprocess", "depth_order_scan", "binning", "blend_forward", "blend_backward", "gaussian_backward")):
+        n = lib.gsr_profile_read(sid, buf.ctypes.data, 256)
+        stage_ms[name] = float(buf[:n].mean()) if n > 0 else None
+    lib.gsr_profile_enable(0)
+    ms_per_step = ms / args.steps
+    value = world * 1000.0 / ms_per_step
+    R = int(info["R"])
+    V = int((info["radii"] > 0).sum().item())
+
+    # ---- end to end through the public API, inputs from pinned host memory every step ----
+    keys = ("means3D", "colors", "opacities", "uncertainties", "scales", "rotations")
+    host = {k: scene_cpu[k].pin_memory() for k in keys}
+    host_cam = {k: cam_cpu[k].pin_memory() for k in ("viewmatrix", "projmatrix", "campos")}
+    host_grads = [g.pin_memory() for g in grads_cpu]
+    h2d_bytes = sum(t.numel() * 4 for t in host.values()) + sum(t.numel() * 4 for t in host_cam.values()) + sum(g.numel() * 4 for g in host_grads)
+    loss_host = torch.zeros(1).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [dict() for _ in range(2)]                                      # double-buffered device staging
+    for sl in slots:
+        for k in keys:
+            sl[k] = torch.empty_like(scene[k])
+        for k in host_cam:
+            sl[k] = torch.empty_like(cam[k])
+        sl["g"] = [torch.empty_like(g) for g in ups[0]]
+        sl["ready"] = torch.cuda.Event()
+        sl["free"] = torch.cuda.Event()
+        sl["free"].record()
+    state = {"i": 0, "primed": False}
+
+    def upload(sl):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sl["free"])
+            for k in keys:
+                sl[k].copy_(host[k], non_blocking=True)
+            for k in host_cam:
+                sl[k].copy_(host_cam[k], non_blocking=True)
+            for d, h in zip(sl["g"], host_grads):
+                d.copy_(h, non_blocking=True)
+            sl["ready"].record(copy_stream)
+
+    def e2e_step():
+        # step i consumes slot i%2 (uploaded during step i-1) and starts the upload of step i+1's inputs
+        if not state["primed"]:
+            upload(slots[0])
+            state["primed"] = True
+        sl = slots[state["i"] % 2]
+        upload(slots[(state["i"] + 1) % 2])
+        cur = torch.cuda.current_stream()
+        cur.wait_event(sl["ready"])
+        leaves = {k: sl[k].requires_grad_(True) for k in keys}
+        m2d = torch.zeros_like(sl["means3D"], requires_grad=True)
+        st = ours.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], scene["bg"], 1.0, sl["viewmatrix"], sl["projmatrix"],
+                                                1, sl["campos"], False, False)
+        color, depth, unc, radii = ours.GaussianRasterizer(st)(
+            means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], uncertainties=leaves["uncertainties"],
+            colors_precomp=leaves["colors"], scales=leaves["scales"], rotations=leaves["rotations"])
+        torch.autograd.backward((color, depth, unc), tuple(sl["g"]))
+        loss = (color.detach() * sl["g"][0]).sum() + leaves["means3D"].grad.abs().sum()
+        loss_host.copy_(loss.reshape(1), non_blocking=True)                 # the step's result goes back to the host
+        for k in keys:
+            sl[k].requires_grad_(False)
+            sl[k].grad = None
+        sl["free"].record(cur)
+        state["i"] += 1
+
+    e2e_ms, _ = _timed(e2e_step, args.steps, max(3, args.warmup), world)
+    torch.cuda.synchronize()
+    e2e_value = world * 1000.0 * args.steps / e2e_ms
+
+    out = None
+    if rank == 0:
+        peak, peak_src = _peaks()
+        bytes_bwd = algorithmic_bytes_blend_backward(C, W, H, R, V)
+        t_bwd = stage_ms["blend_backward"]
+        achieved = bytes_bwd / (t_bwd * 1e-3) / 1e9 if t_bwd else None
+        out = {
+            "metric": "fwd+bwd views/sec", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded Gaussian cloud, SURVEY.md 8d; one camera view per GPU)",
+            "config": {"workload": "%s: %d Gaussians, %dx%d, %d feature channels + depth + uncertainty, fwd+bwd" % (args.workload, P, W, H, C),
+                       "views_per_step": world, "num_rendered": R, "visible": V, "parallelism": "view-parallel dp%d" % world,
+                       "l2": "working set (features 128 MB + records 64 MB + planes 282 MB x2) exceeds the 126 MB L2; no explicit flush",
+                       "collective": "1 NCCL sum-allreduce of the %.0f MB gradient bucket per step" % (bucket.nbytes() / 1e6) if world > 1 else "none (1 GPU)"},
+            "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "note": "public GaussianRasterizer API + autograd; all Gaussian arrays, camera and upstream gradient planes copied from pinned host memory every step (double-buffered on a copy stream); loss scalar read back"},
+            "gpu_launches": launches, "clocks": clocks,
+            "stage_ms": stage_ms,
+            "roofline": {"bound": "hbm", "kernel": "gsr::blend_backward_kernel<%d>" % C, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None, "algorithmic_bytes_per_launch": bytes_bwd,
+                         "avg_launch_ms": t_bwd, "peak_source": peak_src,
+                         "note": "blend kernels are FP32-issue bound, not HBM bound (see DESIGN.md / profiles/)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_port(cfg)
+    return out
+
+
+def run_reference(args, cfg, rank, world, local):
+    """The reference's own CUDA build through its own Python API (rank 0 only)."""
+    if rank != 0:
+        return None
+    import _ref_utils as ru
+    from gscream_b200 import scenes
+    P, W, H, C, seed = cfg["P"], cfg["W"], cfg["H"], cfg["C"], cfg["seed"]
+    if not ru.ref_available(C):
+        return {"impl": "reference", "unavailable": "oracle/_ref/dgr%d not built (oracle/build_ref.py needs /root/reference)" % C}
+    ref = ru.load_ref(C)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    scene = {k: v.to(dev) for k, v in scenes.make_scene(P, W, H, C, seed).items()}
+    cam = scenes.make_camera(W, H)
+    gc, gd, gu = (g.to(dev) for g in scenes.make_upstream_grads(C, W, H, seed))
+    st = ref.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=scene["bg"],
+                                           scale_modifier=1.0, viewmatrix=cam["viewmatrix"].to(dev), projmatrix=cam["projmatrix"].to(dev),
+                                           sh_degree=1, campos=cam["campos"].to(dev), prefiltered=False, debug=False)
+    rast = ref.GaussianRasterizer(raster_settings=st)
+    leaves = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "colors", "opacities", "uncertainties", "scales", "rotations")}
+    m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+
+    def step():
+        color, depth, unc, radii = rast(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], uncertainties=leaves["uncertainties"],
+                                        shs=None, colors_precomp=leaves["colors"], scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None)
+        torch.autograd.backward((color, depth, unc), (gc, gd, gu))
+        for t in list(leaves.values()) + [m2d]:
+            t.grad = None
+
+    ms, clocks = _timed(step, args.steps, args.warmup, 1, ClockSampler(local))
+    ms_per_step = ms / args.steps
+    value = 1000.0 / ms_per_step
+    cores = os.cpu_count()
+    sample = "full workload, %d steps: the reference has no CPU rasterizer; its CUDA sources (unmodified, NUM_CHANNELS=%d via pre-include) recompiled for sm_100a, 1 GPU, device-resident inputs" % (args.steps, C)
+    return {"impl": "reference", "metric": "fwd+bwd views/sec", "value": value, "unit": "views/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded Gaussian cloud, SURVEY.md 8d)",
+            "config": {"workload": "%s: %d Gaussians, %dx%d, %d feature channels + depth + uncertainty, fwd+bwd" % (args.workload, P, W, H, C)},
+            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "clocks": clocks}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config2", "config3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    from gscream_b200 import scenes
+    cfg = scenes.CONFIGS[args.workload]
+    rank, world, local = _dist_env()
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args, cfg, rank, world, local)), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    out = run_ours(args, cfg, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

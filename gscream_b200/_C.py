@@ -54,6 +54,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, uncertaintys, scal
     (num_rendered, color[C,H,W], depth[1,H,W], uncertainty[1,H,W], radii[P], geomBuffer, binningBuffer, imgBuffer)."""
     lib = _lib.load()
     _check_means(means3D)
+    if not means3D.is_cuda:
+        raise ValueError("means3D must be a CUDA tensor (there is no CPU rasterizer)")
     P, H, W = means3D.size(0), int(image_height), int(image_width)
     dev = means3D.device
     with torch.cuda.device(dev):
@@ -153,7 +155,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             if debug:
                 torch.cuda.synchronize(dev)
     return (out["dL_dmeans2D"], out["dL_dcolors"], out["dL_dopacity"], out["dL_duncertainty"], out["dL_dmeans3D"],
-            out["dL_dcov3D"], out["dL_dsh"], out["dL_dscales"], out["dL_drotations"])
+            out.get("dL_dcov3D"), out.get("dL_dsh"), out["dL_dscales"], out["dL_drotations"])
 
 
 def _filter_common(means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix):
@@ -166,6 +168,7 @@ def rasterize_aussians_filter(means3D, scales, rotations, scale_modifier, cov3D_
                               tan_fovx, tan_fovy, image_height, image_width, prefiltered, debug):
     """RasterizeGaussiansfilterCUDA (sic), rasterize_points.cu:235-299 -> radii[P] int32."""
     lib = _lib.load()
+    _check_means(means3D)
     dev = means3D.device
     with torch.cuda.device(dev):
         means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix = _filter_common(
@@ -186,6 +189,7 @@ def rasterize_aussians_filter_position2D(means3D, scales, rotations, scale_modif
                                          tan_fovx, tan_fovy, image_height, image_width, prefiltered, debug):
     """RasterizeGaussiansfilterPositionCUDA, rasterize_points.cu:304-373 -> (radii, x, y)."""
     lib = _lib.load()
+    _check_means(means3D)
     dev = means3D.device
     with torch.cuda.device(dev):
         means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix = _filter_common(

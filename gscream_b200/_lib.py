@@ -29,6 +29,8 @@ PROTOTYPES = {
     "gsr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gsr_debug_export": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_launch_count": (_i64, [_i]),
+    "gsr_profile_enable": (_i, [_i]),
+    "gsr_profile_read": (_i, [_i, _vp, _i]),
 }
 
 _LIB = None

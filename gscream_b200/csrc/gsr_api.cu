@@ -12,6 +12,27 @@ namespace gsr {
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional per-stage device timing (bench.py's roofline line) ---------------------------------
+// When enabled, every stage launch is bracketed by a cudaEvent pair on the caller's stream (a ring of
+// kProfCap pairs per stage).  Nothing is synchronised here; gsr_profile_read() is called after the
+// caller's own synchronise.  Disabled (the default) it costs one branch per stage.
+enum Stage { kPre = 0, kDepthScan, kBin, kBlendFwd, kBlendBwd, kPreBwd, kNumStages };
+static constexpr int kProfCap = 256;
+static bool g_prof_on = false;
+static cudaEvent_t g_ev[kNumStages][kProfCap][2];
+static int g_ev_n[kNumStages];
+static bool g_ev_made = false;
+struct StageTimer {
+	cudaStream_t s; int st; int slot;
+	StageTimer(int stage, cudaStream_t stream) : s(stream), st(stage), slot(-1)
+	{
+		if (!g_prof_on || g_ev_n[st] >= kProfCap) return;
+		slot = g_ev_n[st]++;
+		cudaEventRecord(g_ev[st][slot][0], s);
+	}
+	~StageTimer() { if (slot >= 0) cudaEventRecord(g_ev[st][slot][1], s); }
+};
+
 // implemented in the other translation units
 struct PreArgs {
 	int P, C, D, M;
@@ -152,8 +173,8 @@ int gsr_forward_stage1(int P, int C, int sh_degree, int M, const float *means3D,
 	a.depth_val = (uint32_t *)(geom + L.depth_val[0]);
 	a.clamped = (uint8_t *)(geom + L.clamped);
 	a.rgb = (float *)(geom + L.rgb);
-	GSR_CUDA(launch_preprocess(0, a, stream));
-	GSR_CUDA(depth_order_and_scan(P, geom, L, stream));
+	{ StageTimer t(kPre, stream); GSR_CUDA(launch_preprocess(0, a, stream)); }
+	{ StageTimer t(kDepthScan, stream); GSR_CUDA(depth_order_and_scan(P, geom, L, stream)); }
 	// R = offsets[P-1]: 4 bytes into the low half of the (pre-zeroed, little-endian) int64
 	GSR_CUDA(cudaMemcpyAsync(num_rendered_host, geom + L.offsets + (size_t)(P - 1) * 4, 4, cudaMemcpyDeviceToHost, stream));
 	return 0;
@@ -176,10 +197,13 @@ int gsr_forward_stage2(int P, int C, int64_t num_rendered, const float *colors_p
 	if (!aligned16(geom_buffer) || !aligned16(binning_buffer) || !aligned16(image_buffer)) return GSR_E_WORKSPACE;
 	char *geom = (char *)geom_buffer, *binning = (char *)binning_buffer, *image = (char *)image_buffer;
 
-	GSR_CUDA(bin_instances(P, num_rendered, width, height, geom, GL, binning, BL, image, IL, stream));
-	GSR_CUDA(launch_blend_forward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[1]),
-	                              (const float *)(geom + GL.rec), colors_precomp, background, (float *)(image + IL.final_T),
-	                              (uint32_t *)(image + IL.n_contrib), out_color, out_depth, out_uncertainty, stream));
+	{ StageTimer t(kBin, stream); GSR_CUDA(bin_instances(P, num_rendered, width, height, geom, GL, binning, BL, image, IL, stream)); }
+	{
+		StageTimer t(kBlendFwd, stream);
+		GSR_CUDA(launch_blend_forward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[1]),
+		                              (const float *)(geom + GL.rec), colors_precomp, background, (float *)(image + IL.final_T),
+		                              (uint32_t *)(image + IL.n_contrib), out_color, out_depth, out_uncertainty, stream));
+	}
 	return 0;
 }
 
@@ -216,6 +240,7 @@ int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const
 	if (!accumulate || shs) GSR_CUDA(cudaMemsetAsync(dL_dcolors, 0, (size_t)P * C * sizeof(float), stream));
 	count_launch(2);
 	if (num_rendered > 0) {
+		StageTimer t(kBlendBwd, stream);
 		GSR_CUDA(launch_blend_backward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[1]),
 		                               (const float *)(geom + GL.rec), colors_precomp, background, (const float *)(image + IL.final_T),
 		                               (const uint32_t *)(image + IL.n_contrib), dL_dout_color, dL_dout_depth, dL_dout_uncertainty, gacc,
@@ -236,8 +261,30 @@ int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const
 	a.dL_dmeans2D = dL_dmeans2D; a.dL_dopacity = dL_dopacity; a.dL_duncertainty = dL_duncertainty; a.dL_dcolors = dL_dcolors;
 	a.dL_dmeans3D = dL_dmeans3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drotations = dL_drotations;
 	a.accumulate = accumulate;
-	GSR_CUDA(launch_preprocess_backward(a, stream));
+	{ StageTimer t(kPreBwd, stream); GSR_CUDA(launch_preprocess_backward(a, stream)); }
 	return 0;
+}
+
+int gsr_profile_enable(int on)
+{
+	if (on && !g_ev_made) {
+		for (int s = 0; s < kNumStages; s++)
+			for (int i = 0; i < kProfCap; i++)
+				for (int k = 0; k < 2; k++) GSR_CUDA(cudaEventCreate(&g_ev[s][i][k]));
+		g_ev_made = true;
+	}
+	for (int s = 0; s < kNumStages; s++) g_ev_n[s] = 0;
+	g_prof_on = on != 0;
+	return 0;
+}
+
+int gsr_profile_read(int stage, float *ms_host, int capacity)
+{
+	if (stage < 0 || stage >= kNumStages || !ms_host || !g_ev_made) return GSR_E_BADARG;
+	int n = g_ev_n[stage] < capacity ? g_ev_n[stage] : capacity;
+	for (int i = 0; i < n; i++)
+		if (cudaEventElapsedTime(&ms_host[i], g_ev[stage][i][0], g_ev[stage][i][1]) != cudaSuccess) return GSR_E_BADARG;
+	return n;
 }
 
 static int run_filter(int mode, int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,

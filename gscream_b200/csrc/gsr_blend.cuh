@@ -20,6 +20,17 @@ struct BlendTraits {
 	static constexpr size_t kSmemBytes = kStageBytes + kWarpsPerTile * kBatch + kBatch;
 };
 
+// power = -0.5 (a dx^2 + c dy^2) - b dx dy, CR/forward.cu:524 / CR/backward.cu:524, with the rounding
+// sequence of the reference build's SASS (same in renderCUDA forward and backward, C = 3 and 32):
+//   s = fma(dx, a*dx, (c*dy)*dy) ; power = fma(s, -0.5, -((b*dx)*dy))
+// pinned with explicit intrinsics: a 1-ulp change of alpha can flip the 1/255 and 1e-4 threshold tests
+// and with them n_contrib.
+__device__ __forceinline__ float gaussian_power(float a, float b, float c, float dx, float dy)
+{
+	const float s = __fmaf_rn(dx, __fmul_rn(a, dx), __fmul_rn(__fmul_rn(c, dy), dy));
+	return __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(b, dx), dy));
+}
+
 // Pixel owned by (warp, lane): warps tile the 16x16 block as 2 (x) by 4 (y) blocks of 8x4 pixels.
 __device__ __forceinline__ void warp_block_origin(int warp, int &bx, int &by)
 {

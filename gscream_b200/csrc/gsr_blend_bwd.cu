@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 			const float4 r0 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS);     // x y a b
 			const float4 r1 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 4); // c o depth unc
 			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
-			const float power = -0.5f * (r0.z * d.x * d.x + r1.x * d.y * d.y) - r0.w * d.x * d.y;
-			const float G = exp(power);
-			const float alpha = min(0.99f, r1.y * G);
+			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
+			const float G = expf(power);
+			const float alpha = min(0.99f, __fmul_rn(r1.y, G));
 			const bool valid = (pos < last_contributor) && !(power > 0.0f) && !(alpha < kAlphaMin);
 			if (!__any_sync(0xffffffffu, valid)) continue;
 
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 			for (int i = 0; i < NV; i++) v[i] = 0.f;
 			float w = 0.f;
 			if (valid) {
-				T = T / (1.f - alpha);
+				T = __fdiv_rn(T, __fsub_rn(1.f, alpha));
 				w = alpha * T;
 				// dot = f_j . g_p over colour channels, depth and uncertainty
 				float dot = r1.z * gd + r1.w * gu;

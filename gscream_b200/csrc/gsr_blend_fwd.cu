@@ -100,11 +100,11 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
 			const float4 r1 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 4); // c o depth unc
 			// same expression as CR/forward.cu:521-525
 			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
-			const float power = -0.5f * (r0.z * d.x * d.x + r1.x * d.y * d.y) - r0.w * d.x * d.y;
+			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
 			if (done || power > 0.0f) continue;
-			const float alpha = min(0.99f, r1.y * exp(power));
+			const float alpha = min(0.99f, __fmul_rn(r1.y, expf(power)));
 			if (alpha < kAlphaMin) continue;
-			const float test_T = T * (1 - alpha);
+			const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
 			if (test_T < 0.0001f) {
 				done = true;
 				continue;

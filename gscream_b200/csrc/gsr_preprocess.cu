@@ -69,12 +69,27 @@ __device__ __forceinline__ float4 xform4x4(const float3 &p, const float *m)
 
 __device__ __forceinline__ M3 rotation_of(const float4 q)
 {
-	// CR/forward.cu:130-140 — quaternion used as given (r,x,y,z), no normalisation (:129)
-	float r = q.x, x = q.y, y = q.z, z = q.w;
+	// CR/forward.cu:130-140 — quaternion used as given (r,x,y,z), no normalisation (:129).
+	// The mixed terms a*b +- c*d are where ptxas (not nvcc's front end) picks which product to keep rounded
+	// and which to fuse; the choice below is the one in the reference build's SASS for sm_100a (identical in
+	// preprocessCUDA, filter_preprocessCUDA and position2D_preprocessCUDA), pinned with explicit
+	// round-to-nearest intrinsics so that it cannot drift with code motion in this kernel.
+	const float r = q.x, x = q.y, y = q.z, z = q.w;
+	const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x), rz = __fmul_rn(r, z);
+	const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+	const float xz_p_ry = __fmaf_rn(r, y, xz);   // x*z + r*y
+	const float xz_m_ry = __fmaf_rn(-r, y, xz);  // x*z - r*y
+	const float yz_m_rx = __fmaf_rn(y, z, -rx);  // y*z - r*x
+	const float yz_p_rx = __fmaf_rn(y, z, rx);   // y*z + r*x
+	const float xy_m_rz = __fmaf_rn(x, y, -rz);  // x*y - r*z
+	const float xy_p_rz = __fmaf_rn(x, y, rz);   // x*y + r*z
+	const float yy_zz = __fadd_rn(yy, zz);
+	const float xx_zz = __fmaf_rn(x, x, zz);
+	const float xx_yy = __fmaf_rn(x, x, yy);
 	M3 R;
-	R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z);       R.m[0][2] = 2.f * (x * z + r * y);
-	R.m[1][0] = 2.f * (x * y + r * z);       R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
-	R.m[2][0] = 2.f * (x * z - r * y);       R.m[2][1] = 2.f * (y * z + r * x);       R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+	R.m[0][0] = __fsub_rn(1.f, __fadd_rn(yy_zz, yy_zz)); R.m[0][1] = __fadd_rn(xy_m_rz, xy_m_rz);             R.m[0][2] = __fadd_rn(xz_p_ry, xz_p_ry);
+	R.m[1][0] = __fadd_rn(xy_p_rz, xy_p_rz);             R.m[1][1] = __fsub_rn(1.f, __fadd_rn(xx_zz, xx_zz)); R.m[1][2] = __fadd_rn(yz_m_rx, yz_m_rx);
+	R.m[2][0] = __fadd_rn(xz_m_ry, xz_m_ry);             R.m[2][1] = __fadd_rn(yz_p_rx, yz_p_rx);             R.m[2][2] = __fsub_rn(1.f, __fadd_rn(xx_yy, xx_yy));
 	return R;
 }
 
@@ -271,14 +286,16 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 		c.cov.m[1][1] += 0.3f;
 		const float3 cov = {float(c.cov.m[0][0]), float(c.cov.m[0][1]), float(c.cov.m[1][1])};
 
-		float det = (cov.x * cov.z - cov.y * cov.y);
+		// det and mid^2 - det: fused as in the reference build's SASS (FMUL cov.y^2 ; FFMA cov.x*cov.z - .)
+		float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
 		if (det != 0.0f) {
 			float det_inv = 1.f / det;
 			float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
 
 			float mid = 0.5f * (cov.x + cov.z);
-			float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
-			float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+			const float disc = max(0.1f, __fmaf_rn(mid, mid, -det));
+			float lambda1 = mid + sqrt(disc);
+			float lambda2 = mid - sqrt(disc);
 			float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
 			float2 point_image = {ndc2pix(p_proj.x, a.W), ndc2pix(p_proj.y, a.H)};
 			int x0, y0, x1, y1;

@@ -159,6 +159,17 @@ GSR_API int gsr_debug_export(
     uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib,
     gsr_stream_t stream);
 
+/*
+ * Optional per-stage device timing for benchmarks.  gsr_profile_enable(1) (re)starts recording: every stage
+ * launch is bracketed by a cudaEvent pair on the caller's stream (up to 256 per stage, nothing is
+ * synchronised); gsr_profile_enable(0) stops.  After the caller has synchronised, gsr_profile_read() copies the
+ * elapsed milliseconds of the recorded launches of one stage to HOST memory and returns how many there were.
+ * Stages: 0 preprocess, 1 depth order + scan, 2 instance binning, 3 blend forward, 4 blend backward,
+ * 5 per-Gaussian backward.
+ */
+GSR_API int gsr_profile_enable(int on);
+GSR_API int gsr_profile_read(int stage, float *ms_host, int capacity);
+
 /* Number of this library's kernel launches since the last call with reset != 0
  * (bench.py reports it as `gpu_launches`). */
 GSR_API int64_t gsr_launch_count(int reset);

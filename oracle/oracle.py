@@ -67,7 +67,7 @@ class Oracle:
             radii=np.zeros(P, np.int32),
             xy=np.zeros((P, 2), r), depths=np.zeros(P, r), cov3D=np.zeros((P, 6), r),
             conic_opacity=np.zeros((P, 4), r), tiles_touched=np.zeros(P, np.uint32),
-            uncertainty=np.zeros(P, r), pos2d_x=np.zeros(P, r), pos2d_y=np.zeros(P, r),
+            gauss_uncertainty=np.zeros(P, r), pos2d_x=np.zeros(P, r), pos2d_y=np.zeros(P, r),
         )
         scales, rotations = _f32(scales), _f32(rotations)
         cov3D_precomp = _f32(cov3D_precomp)
@@ -79,7 +79,7 @@ class Oracle:
             _p(rotations), _p(opac.reshape(-1)), _p(unc.reshape(-1)), _p(cov3D_precomp), _p(view), _p(proj),
             ctypes.c_int(W), ctypes.c_int(H), ctypes.c_float(tanfovx), ctypes.c_float(tanfovy),
             _p(out["radii"]), _p(out["xy"]), _p(out["depths"]), _p(out["cov3D"]), _p(out["conic_opacity"]),
-            _p(out["tiles_touched"]), _p(out["uncertainty"]), _p(out["pos2d_x"]), _p(out["pos2d_y"]))
+            _p(out["tiles_touched"]), _p(out["gauss_uncertainty"]), _p(out["pos2d_x"]), _p(out["pos2d_y"]))
         if cov3D_precomp is not None:
             out["cov3D"] = cov3D_precomp.astype(r)
         return out
@@ -138,11 +138,12 @@ class Oracle:
         binn = self.binning(pre["xy"], pre["depths"], pre["radii"], W, H)
         # the reference stores fp32 intermediates; the f64 oracle keeps them in double on purpose
         img = self.render_forward(W, H, binn["ranges"], binn["point_list"], pre["xy"], colors_precomp,
-                                  pre["depths"], pre["uncertainty"], pre["conic_opacity"], bg)
+                                  pre["depths"], pre["gauss_uncertainty"], pre["conic_opacity"], bg)
         out = {}
-        out.update(pre)
-        out.update(binn)
-        out.update(img)
+        for part in (pre, binn, img):
+            for k, v in part.items():
+                assert k not in out, "oracle stage outputs must not shadow each other: %s" % k
+                out[k] = v
         return out
 
     # -- K7 + K8 + K9 (Rasterizer::backward, rasterizer_impl.cu:536-643) ---------------------
@@ -161,7 +162,7 @@ class Oracle:
         rg = np.ascontiguousarray(fwd["ranges"], dtype=np.uint32)
         pl = np.ascontiguousarray(fwd["point_list"], dtype=np.uint32)
         nc = np.ascontiguousarray(fwd["n_contrib"], dtype=np.uint32)
-        xy, co, dep, unc, fT, bg_ = a(fwd["xy"]), a(fwd["conic_opacity"]), a(fwd["depths"]), a(fwd["uncertainty"]), a(fwd["final_T"]), a(bg)
+        xy, co, dep, unc, fT, bg_ = a(fwd["xy"]), a(fwd["conic_opacity"]), a(fwd["depths"]), a(fwd["gauss_uncertainty"]), a(fwd["final_T"]), a(bg)
         gc, gd, gu = a(dL_dcolor), a(dL_ddepth), a(dL_dunc)
         self.lib.orc_render_backward(ctypes.c_int(C), ctypes.c_int(W), ctypes.c_int(H), _p(rg), _p(pl), _p(bg_), _p(xy),
                                      _p(co), _p(colors), _p(dep), _p(unc), _p(fT), _p(nc), _p(gc), _p(gd), _p(gu),

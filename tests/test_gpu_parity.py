@@ -1,0 +1,295 @@
+"""GPU (-m gpu): parity of the CUDA product, called through the reference-facing surface
+(GaussianRasterizer -> gscream_b200._C -> C ABI of libgsr_b200.so), against
+  (1) golden vectors from the reference's own CUDA build (tests/golden/*.npz),
+  (2) the CPU oracle on fresh seeded inputs and the edge cases the reference's code paths distinguish,
+  (3) the reference's own CUDA build itself (oracle/_ref, travels with the repo) at BASELINE.json's full sizes,
+  (4) size-independent properties at full size.
+Bars: integer / index artefacts (radii, tiles_touched, R, point_list, ranges, n_contrib) and the fp32 projection
+(xy, depth, conic) bit-exact; rendered planes and gradients within 1e-5 of the plane's scale
+(+ the reference's measured atomic run-to-run spread for gradients)."""
+import numpy as np
+import pytest
+import torch
+
+import _ref_utils as ru
+from _cases import GOLDEN_CASES, GRAD_KEYS, load_golden
+from gscream_b200 import _C, _lib, scenes
+from gscream_b200 import rasterizer as ours
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _require_native():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _lib.load()  # raises if libgsr_b200.so is missing: no silent fallback
+
+
+def _scene_from_golden(g):
+    scene = {k[3:]: torch.from_numpy(g[k]) for k in g if k.startswith("in_")}
+    cam = dict(W=int(g["W"]), H=int(g["H"]), tanfovx=float(g["cam_tanfovx"]), tanfovy=float(g["cam_tanfovy"]),
+               viewmatrix=torch.from_numpy(g["cam_viewmatrix"]), projmatrix=torch.from_numpy(g["cam_projmatrix"]),
+               campos=torch.from_numpy(g["cam_campos"]))
+    grads = tuple(torch.from_numpy(g[k]) for k in ("g_color", "g_depth", "g_unc"))
+    return scene, cam, grads
+
+
+def _export(m, P, W, H):
+    e = _C.debug_export(P, m["num_rendered"], W, H, m["_geom"], m["_binning"], m["_img"])
+    return {k: v.cpu().numpy() for k, v in e.items()}
+
+
+def _check_ints_and_projection(m, e, ref_radii, ref_geom, ref_img, ref_plist, R):
+    vis = ref_radii > 0
+    assert m["num_rendered"] == R
+    assert np.array_equal(m["radii"], ref_radii)
+    assert np.array_equal(e["tiles_touched"].view(np.uint32), ref_geom["tiles_touched"])
+    assert np.array_equal(e["xy"][vis].view(np.uint32), ref_geom["means2D"][vis].view(np.uint32))
+    assert np.array_equal(e["depths"][vis].view(np.uint32), ref_geom["depths"][vis].view(np.uint32))
+    assert np.array_equal(e["conic_opacity"][vis].view(np.uint32), ref_geom["conic_opacity"][vis].view(np.uint32))
+    assert np.array_equal(e["point_list"].view(np.uint32), ref_plist)
+    assert np.array_equal(e["ranges"].view(np.uint32), ref_img["ranges"])
+    assert np.array_equal(e["n_contrib"].view(np.uint32), ref_img["n_contrib"])
+    assert np.array_equal(e["final_T"].view(np.uint32), ref_img["final_T"].view(np.uint32))  # same alpha chain, bit for bit
+
+
+def _check_floats(m, ref, spread=None):
+    for k in ("color", "depth", "uncertainty"):
+        tol = REL * np.abs(ref[k]).max()
+        assert np.abs(m[k] - ref[k]).max() <= tol, (k, float(np.abs(m[k] - ref[k]).max()), float(tol))
+    for k in GRAD_KEYS:
+        rel = REL if k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_duncertainty") else 3 * REL
+        tol = rel * np.abs(ref[k]).max() + (8.0 * spread[k] if spread else 0.0)
+        assert np.abs(m[k] - ref[k]).max() <= tol, (k, float(np.abs(m[k] - ref[k]).max()), float(tol))
+        assert not m[k][ref["radii"] == 0].any()  # culled Gaussians: exactly zero
+
+
+# ---- (1) golden vectors of the reference build ---------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_against_reference_golden(name):
+    _require_native()
+    g = load_golden(name)
+    scene, cam, grads = _scene_from_golden(g)
+    P, W, H = int(g["P"]), cam["W"], cam["H"]
+    m = ru.run_impl(ours, scene, cam, grads)
+    e = _export(m, P, W, H)
+    geom = dict(tiles_touched=g["geom_tiles_touched"], means2D=g["geom_means2D"], depths=g["geom_depths"], conic_opacity=g["geom_conic_opacity"])
+    img = dict(ranges=g["img_ranges"], n_contrib=g["img_n_contrib"], final_T=g["img_final_T"])
+    _check_ints_and_projection(m, e, g["radii"], geom, img, g["bin_point_list"], int(g["num_rendered"]))
+    ref = {k: g[k] for k in ["color", "depth", "uncertainty", "radii"] + GRAD_KEYS}
+    spread = {k: float(np.abs(g["rerun_" + k] - g[k]).max()) for k in GRAD_KEYS}
+    _check_floats(m, ref, spread)
+
+
+# ---- (2) CPU oracle on fresh inputs and edge cases ------------------------------------------------------------
+def _oracle_run(scene, cam, grads, prec="f64"):
+    from oracle.oracle import Oracle
+    o = Oracle(prec)
+    a = dict(means3D=scene["means3D"].numpy(), colors_precomp=scene["colors"].numpy(), opacities=scene["opacities"].numpy(),
+             uncertainties=scene["uncertainties"].numpy(), scales=scene["scales"].numpy(), rotations=scene["rotations"].numpy(),
+             viewmatrix=cam["viewmatrix"].numpy(), projmatrix=cam["projmatrix"].numpy(), bg=scene["bg"].numpy(), W=cam["W"], H=cam["H"],
+             tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"])
+    f = o.forward(**a)
+    b = o.backward(f, means3D=a["means3D"], colors_precomp=a["colors_precomp"], scales=a["scales"], rotations=a["rotations"],
+                   viewmatrix=a["viewmatrix"], projmatrix=a["projmatrix"], bg=a["bg"], W=a["W"], H=a["H"], tanfovx=a["tanfovx"],
+                   tanfovy=a["tanfovy"], dL_dcolor=grads[0].numpy(), dL_ddepth=grads[1].numpy(), dL_dunc=grads[2].numpy())
+    return f, b
+
+
+ORACLE_KEY = {"dL_dmeans3D": "dL_dmeans3D", "dL_dmeans2D": "dL_dmean2D", "dL_dcolors": "dL_dcolors", "dL_dopacity": "dL_dopacity",
+              "dL_duncertainty": "dL_duncertainty", "dL_dscales": "dL_dscales", "dL_drotations": "dL_drotations"}
+
+
+@pytest.mark.parametrize("P,W,H,C,seed,smult,yaw", [
+    (3000, 200, 120, 3, 101, 1.5, 0.0),
+    (2000, 131, 77, 3, 102, 3.0, 12.0),      # ragged image, yawed camera, big splats
+    (2500, 144, 96, 32, 103, 1.5, 0.0),
+    (1500, 97, 65, 32, 104, 4.0, -9.0),      # ragged, long lists (several 256-batches per tile)
+    (1, 64, 64, 3, 105, 6.0, 0.0),           # a single Gaussian
+    (300, 16, 16, 32, 106, 2.0, 0.0),        # a single tile
+])
+def test_against_cpu_oracle(P, W, H, C, seed, smult, yaw):
+    _require_native()
+    scene = scenes.make_scene(P, W, H, C, seed, scale_mult=smult, bg_value=0.2 if C == 3 else 0.0)
+    cam = scenes.make_camera(W, H, yaw_deg=yaw)
+    grads = scenes.make_upstream_grads(C, W, H, seed)
+    m = ru.run_impl(ours, scene, cam, grads)
+    f, b = _oracle_run(scene, cam, grads, "f64")
+    e = _export(m, P, W, H)
+    # integers: identical unless a float sits within rounding of a ceil()/trunc() boundary; on these seeds none does
+    assert np.array_equal(m["radii"], f["radii"])
+    assert m["num_rendered"] == f["num_rendered"]
+    assert np.array_equal(e["point_list"].view(np.uint32), f["point_list"])
+    assert np.array_equal(e["ranges"].view(np.uint32), f["ranges"])
+    flips = int((e["n_contrib"].view(np.uint32) != f["n_contrib"]).sum())
+    assert flips <= 3  # GPU expf vs libm exp at a 1/255 or 1e-4 threshold
+    for k in ("color", "depth", "uncertainty"):
+        bad = (np.abs(m[k] - f[k]) > 2 * REL * max(np.abs(f[k]).max(), 1e-3)).any(axis=0)
+        assert int(bad.sum()) <= 3, k
+    for k in GRAD_KEYS:
+        ref = b[ORACLE_KEY[k]]
+        ref = ref.reshape(m[k].shape) if ref.size == m[k].size else ref[:, :m[k].shape[1]]
+        scale = np.abs(ref).max()
+        rel = (2 * REL if k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_duncertainty") else 1e-4)
+        tol = rel * scale + (1e-3 * scale if flips else 0.0) + 1e-12
+        assert np.abs(m[k] - ref).max() <= tol, (k, float(np.abs(m[k] - ref).max()), float(tol))
+
+
+def test_empty_and_fully_culled_inputs():
+    _require_native()
+    dev = torch.device("cuda")
+    W, H = 48, 32
+    cam = scenes.make_camera(W, H)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    st = ours.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], bg, 1.0, cam["viewmatrix"].to(dev),
+                                            cam["projmatrix"].to(dev), 1, cam["campos"].to(dev), False, False)
+    rast = ours.GaussianRasterizer(st)
+    # P == 0: zero images and empty radii, no launch (rasterize_points.cu:85)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    color, depth, unc, radii = rast(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1), uncertainties=z(0, 1),
+                                    colors_precomp=z(0, 3), scales=z(0, 3), rotations=z(0, 4))
+    assert color.shape == (3, H, W) and not color.any() and radii.numel() == 0
+    # all Gaussians behind the camera: background only, zero gradients
+    P = 9
+    means = z(P, 3)
+    means[:, 2] = -1.0
+    means.requires_grad_(True)
+    cols = torch.rand(P, 3, device=dev, requires_grad=True)
+    color, depth, unc, radii = rast(means3D=means, means2D=z(P, 3), opacities=torch.full((P, 1), 0.5, device=dev), uncertainties=z(P, 1),
+                                    colors_precomp=cols, scales=torch.full((P, 3), 0.1, device=dev),
+                                    rotations=torch.tensor([[1.0, 0, 0, 0]], device=dev).repeat(P, 1))
+    assert not radii.any() and torch.allclose(color, bg[:, None, None].expand_as(color)) and not depth.any() and not unc.any()
+    (color.sum() + depth.sum()).backward()
+    assert not means.grad.any() and not cols.grad.any()
+
+
+def test_precomputed_covariance_path_matches_scale_rotation_path():
+    """cov3D_precomp (gaussian_renderer's compute_cov3D_python option): same images; dL_dcov3D returned."""
+    _require_native()
+    dev = torch.device("cuda")
+    P, W, H, C = 2000, 160, 96, 3
+    s = {k: v.to(dev) for k, v in scenes.make_scene(P, W, H, C, 201, scale_mult=2.0).items()}
+    cam = scenes.make_camera(W, H)
+    st = ours.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], s["bg"], 1.0, cam["viewmatrix"].to(dev),
+                                            cam["projmatrix"].to(dev), 1, cam["campos"].to(dev), False, False)
+    rast = ours.GaussianRasterizer(st)
+    m2 = torch.zeros(P, 3, device=dev)
+    a = rast(means3D=s["means3D"], means2D=m2, opacities=s["opacities"], uncertainties=s["uncertainties"], colors_precomp=s["colors"],
+             scales=s["scales"], rotations=s["rotations"])
+    # Sigma = R S S^T R^T with the reference's (r,x,y,z) convention (forward.cu:120-154)
+    q = s["rotations"]
+    r, x, y, zq = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    Rm = torch.stack([1 - 2 * (y * y + zq * zq), 2 * (x * y - r * zq), 2 * (x * zq + r * y),
+                      2 * (x * y + r * zq), 1 - 2 * (x * x + zq * zq), 2 * (y * zq - r * x),
+                      2 * (x * zq - r * y), 2 * (y * zq + r * x), 1 - 2 * (x * x + y * y)], 1).view(P, 3, 3)
+    Sig = Rm @ torch.diag_embed(s["scales"] ** 2) @ Rm.transpose(1, 2)
+    cov6 = torch.stack([Sig[:, 0, 0], Sig[:, 0, 1], Sig[:, 0, 2], Sig[:, 1, 1], Sig[:, 1, 2], Sig[:, 2, 2]], 1).contiguous().requires_grad_(True)
+    b = rast(means3D=s["means3D"], means2D=m2, opacities=s["opacities"], uncertainties=s["uncertainties"], colors_precomp=s["colors"],
+             cov3D_precomp=cov6)
+    assert (a[3] != b[3]).sum().item() <= 2  # radii: identical up to fp32 rounding of Sigma at a ceil() boundary
+    assert torch.allclose(a[0], b[0], atol=2e-3) and torch.allclose(a[1], b[1], atol=2e-2)
+    b[0].sum().backward()
+    assert cov6.grad is not None and cov6.grad.shape == (P, 6) and cov6.grad.abs().sum() > 0
+
+
+def test_filters_and_mark_visible_match_forward_and_oracle():
+    _require_native()
+    from oracle.oracle import Oracle
+    dev = torch.device("cuda")
+    P, W, H = 20000, 1008, 567
+    sc = scenes.make_scene(P, W, H, 3, 301, scale_mult=2.0)
+    cam = scenes.make_camera(W, H, yaw_deg=5.0)
+    s = {k: v.to(dev) for k, v in sc.items()}
+    st = ours.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], s["bg"], 1.0, cam["viewmatrix"].to(dev),
+                                            cam["projmatrix"].to(dev), 1, cam["campos"].to(dev), False, False)
+    rast = ours.GaussianRasterizer(st)
+    _, _, _, radii = rast(means3D=s["means3D"], means2D=torch.zeros(P, 3, device=dev), opacities=s["opacities"],
+                          uncertainties=s["uncertainties"], colors_precomp=s["colors"], scales=s["scales"], rotations=s["rotations"])
+    r1 = rast.visible_filter(means3D=s["means3D"], scales=s["scales"], rotations=s["rotations"])
+    r2, x, y = rast.position2D_filter(means3D=s["means3D"], scales=s["scales"], rotations=s["rotations"])
+    assert torch.equal(r1, radii) and torch.equal(r2, radii) and r1.dtype == torch.int32
+    present = rast.markVisible(s["means3D"])
+    assert present.dtype == torch.bool and present[radii > 0].all()
+    o = Oracle("f32")
+    pre = o.preprocess(sc["means3D"].numpy(), sc["scales"].numpy(), sc["rotations"].numpy(), None, None, cam["viewmatrix"].numpy(),
+                       cam["projmatrix"].numpy(), W, H, cam["tanfovx"], cam["tanfovy"], mode=2)
+    assert (pre["radii"] != radii.cpu().numpy()).sum() <= 2  # no-FMA CPU arithmetic vs GPU at a ceil() boundary
+    m = (pre["radii"] > 0) & (radii.cpu().numpy() > 0)
+    assert np.abs(pre["pos2d_x"][m] - x.cpu().numpy()[m]).max() < 1e-3 and np.abs(pre["pos2d_y"][m] - y.cpu().numpy()[m]).max() < 1e-3
+    assert not x[radii == 0].any() and not y[radii == 0].any()
+    assert np.array_equal(o.mark_visible(sc["means3D"].numpy(), cam["viewmatrix"].numpy(), cam["projmatrix"].numpy()), present.cpu().numpy())
+    # the filters are called with a non-contiguous scales[:, :3] slice of a [A,6] tensor (gaussian_renderer/__init__.py:298)
+    wide = torch.cat([s["scales"], s["scales"]], 1)
+    assert torch.equal(rast.visible_filter(means3D=s["means3D"], scales=wide[:, :3], rotations=s["rotations"]), radii)
+
+
+# ---- (3) the reference's own CUDA build at BASELINE.json's full sizes ------------------------------------------
+@pytest.mark.parametrize("cfg", ["config2", "config3"])
+def test_full_size_against_reference_build(cfg):
+    _require_native()
+    c = scenes.CONFIGS[cfg]
+    P, W, H, C, seed = c["P"], c["W"], c["H"], c["C"], c["seed"]
+    if not ru.ref_available(C):
+        pytest.skip("oracle/_ref/dgr%d not built (needs /root/reference at build time)" % C)
+    ref_mod = ru.load_ref(C)
+    scene = scenes.make_scene(P, W, H, C, seed)
+    cam = scenes.make_camera(W, H)
+    grads = scenes.make_upstream_grads(C, W, H, seed)
+    r = ru.run_impl(ref_mod, scene, cam, grads)
+    r2 = ru.run_impl(ref_mod, scene, cam, grads)
+    m = ru.run_impl(ours, scene, cam, grads)
+    R = r["num_rendered"]
+    geom = ru.parse_ref_geom(r["_geom"].cpu().numpy(), P)
+    img = ru.parse_ref_image(r["_img"].cpu().numpy(), W, H)
+    binn = ru.parse_ref_binning(r["_binning"].cpu().numpy(), R)
+    e = _export(m, P, W, H)
+    _check_ints_and_projection(m, e, r["radii"], geom, img, binn["point_list"], R)
+    spread = {k: float(np.abs(r2[k] - r[k]).max()) for k in GRAD_KEYS}
+    _check_floats(m, r, spread)
+
+
+# ---- (4) size-independent properties at full size --------------------------------------------------------------
+def test_properties_at_full_size():
+    _require_native()
+    dev = torch.device("cuda")
+    c = scenes.CONFIGS["config3"]
+    P, W, H, C, seed = c["P"], c["W"], c["H"], c["C"], c["seed"]
+    sc = scenes.make_scene(P, W, H, C, seed)
+    cam = scenes.make_camera(W, H)
+    g1 = scenes.make_upstream_grads(C, W, H, seed)
+    g2 = scenes.make_upstream_grads(C, W, H, seed + 1)
+    a = ru.run_impl(ours, sc, cam, g1)
+    b = ru.run_impl(ours, sc, cam, g1)
+    # forward is deterministic to the bit; every tile range is a sorted, disjoint cover of [0, R)
+    for k in ("color", "depth", "uncertainty", "radii"):
+        assert np.array_equal(a[k], b[k])
+    e = _export(a, P, W, H)
+    rng = e["ranges"].view(np.uint32).astype(np.int64)
+    nz = rng[rng[:, 1] > rng[:, 0]]
+    assert (nz[1:, 0] == nz[:-1, 1]).all() and nz[0, 0] == 0 and nz[-1, 1] == a["num_rendered"]
+    assert a["num_rendered"] == int(e["tiles_touched"].view(np.uint32).astype(np.int64).sum())
+    # depth-sortedness inside every tile: depths along point_list are non-decreasing within a range
+    d = e["depths"][e["point_list"]]
+    brk = np.zeros(len(d), bool)
+    brk[nz[:, 0]] = True
+    assert (np.diff(d)[~brk[1:]] >= 0).all()
+    assert (e["n_contrib"].view(np.uint32).reshape(H, W) <= np.repeat(np.repeat((rng[:, 1] - rng[:, 0]).reshape((H + 15) // 16, (W + 15) // 16), 16, 0), 16, 1)[:H, :W]).all()
+    # backward is linear in the upstream gradient: grad(g1 + g2) == grad(g1) + grad(g2)
+    gsum = tuple(x + y for x, y in zip(g1, g2))
+    c2 = ru.run_impl(ours, sc, cam, g2)
+    cs = ru.run_impl(ours, sc, cam, gsum)
+    for k in GRAD_KEYS:
+        tol = 3 * REL * np.abs(cs[k]).max()
+        assert np.abs(cs[k] - (a[k] + c2[k])).max() <= tol, k
+    # the accumulate mode of the C ABI (used by the multi-GPU bucket) equals the sum of separate backward calls
+    from gscream_b200.dist import GradBucket, render_views_into_bucket
+    s = {k: v.to(dev) for k, v in sc.items()}
+    camd = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in cam.items()}
+    bucket = GradBucket(P, C, device=dev)
+    ups = [tuple(t.to(dev) for t in g1), tuple(t.to(dev) for t in g2)]
+    render_views_into_bucket(s, [camd, camd], ups, bucket)
+    for k, name in (("dL_dmeans3D", "means3D"), ("dL_dcolors", "colors"), ("dL_dopacity", "opacities"), ("dL_dscales", "scales"),
+                    ("dL_drotations", "rotations"), ("dL_dmeans2D", "means2D"), ("dL_duncertainty", "uncertainties")):
+        got = bucket.views[name].cpu().numpy()
+        tol = 3 * REL * np.abs(cs[k]).max()
+        assert np.abs(got - (a[k] + c2[k])).max() <= tol, k
