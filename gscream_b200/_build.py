@@ -21,7 +21,7 @@ FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     # NOTE: no --use_fast_math: tile/key indexing must be bit-exact with the reference build
-]
+] + os.environ.get("GSR_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _digest():

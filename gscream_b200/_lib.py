@@ -41,7 +41,8 @@ class GsrError(RuntimeError):
 
 
 def library_path():
-    return _build.LIB
+    # GSR_LIB_PATH: development aid for A/B-ing differently compiled builds of the same library
+    return os.environ.get("GSR_LIB_PATH") or _build.LIB
 
 
 def load():

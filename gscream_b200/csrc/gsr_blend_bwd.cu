@@ -19,13 +19,24 @@
 //     COLUMN of its warp's 32 pixels in registers, the per-pixel weights alpha*T go through 128 B of
 //     shared memory, and the warp issues a single coalesced 128-B red.global.add per Gaussian.
 //     That is one RED instruction per (warp, Gaussian) where the reference issues 32 x C scalar atomics.
-//   * Same bulk-async slab staging and per-warp bounding-box compaction as the forward kernel, plus a
-//     tile-level skip of everything behind the deepest last contributor.
+//   * Same asynchronous double-buffered slab staging and per-warp bounding-box compaction as the forward
+//     kernel, plus a tile- and warp-level skip of everything behind the deepest last contributor, and a
+//     warp vote on a cheap necessary condition (power >= -log(255 opacity) - eps) before any exp is evaluated.
 //
 // Scalar terms are accumulated into gacc[P][8] = {dmean2D.x, dmean2D.y, dconic.x, dconic.y, dconic.w,
 // dopacity, ddepth, duncertainty}; colours into dL_dcolors[P][C].  Both must be zero (or hold the
 // running sum) on entry.
 #include "gsr_blend.cuh"
+
+#ifndef GSR_BWD_EARLYVOTE
+#define GSR_BWD_EARLYVOTE 0
+#endif
+#ifndef GSR_BWD_RCP
+#define GSR_BWD_RCP 1
+#endif
+#ifndef GSR_BWD_ACC4
+#define GSR_BWD_ACC4 0
+#endif
 
 namespace gsr {
 
@@ -74,22 +85,24 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
     float *__restrict__ gacc, float *__restrict__ dL_dcolors)
 {
 	using TR = BlendTraits<C>;
+	constexpr bool kBulk = GSR_BWD_BULK != 0;
 	constexpr bool kLaneChannel = (C == 32); // colour sums by role switch; otherwise through the butterfly
 	constexpr int NV = kLaneChannel ? 8 : 16;
 	static_assert(kLaneChannel || C <= 8, "butterfly path carries at most 8 colour channels");
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	float *s_rec = reinterpret_cast<float *>(smem_raw);
-	float *s_feat = reinterpret_cast<float *>(smem_raw + (size_t)kBatch * GSR_REC_BYTES);
-	uint8_t *s_list = smem_raw + TR::kStageBytes;
-	uint8_t *s_mask = s_list + kWarpsPerTile * kBatch;
-	__shared__ __align__(8) uint64_t s_bar;
+	uint32_t *s_ids = reinterpret_cast<uint32_t *>(smem_raw + TR::kIdsOff);  // [3][kBatch]
+	uint8_t *s_mask = smem_raw + TR::kMaskOff;                               // [3][kBatch]
+	uint8_t *s_list = smem_raw + TR::kListOff;                               // [8][kBatch]
+	auto stage_rec = [&](int s) { return reinterpret_cast<float *>(smem_raw + (size_t)s * TR::kStageBytes); };
+	auto stage_feat = [&](int s) { return reinterpret_cast<float *>(smem_raw + (size_t)s * TR::kStageBytes + (size_t)kBatch * GSR_REC_BYTES); };
 	__shared__ __align__(16) float s_w[kWarpsPerTile][32];
 	__shared__ int s_red[kWarpsPerTile];
-	__shared__ uint32_t s_ids[kBatch];
 
+	__shared__ __align__(8) uint64_t s_bar[kStages];
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int tile = blockIdx.x;
+	stage_init<C, kBulk>(s_bar, tid);
 	const int tile_x0 = (tile % tiles_x) * GSR_BLOCK_X, tile_y0 = (tile / tiles_x) * GSR_BLOCK_Y;
 	int bx, by;
 	warp_block_origin(warp, bx, by);
@@ -108,10 +121,6 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 #pragma unroll
 	for (int s = 16; s >= 1; s >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, s));
 	if (lane == 0) s_red[warp] = warp_last;
-	if (tid == 0) {
-		mbar_init(&s_bar, 1);
-		mbar_fence_init();
-	}
 	__syncthreads();
 	int total = 0;
 #pragma unroll
@@ -159,40 +168,55 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 	float T = T_final;
 	float X = 0.f, last_alpha = 0.f, last_dot = 0.f;
 	const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
+	const float neg_Tfinal_bg = -T_final * bg_dot; // background term: (-T_final / (1 - alpha)) * sum_ch bg[ch] g[ch]
 
-	// staged slot t of round r holds list position total-1-(r*256+t): back to front (CR/backward.cu:500)
-	uint32_t next_id = (tid < total) ? point_list[range.x + (uint32_t)(total - 1 - tid)] : 0u;
+	// staged slot t of batch b holds list position total-1-(b*kBatch+t): back to front (CR/backward.cu:500)
+	auto load_id = [&](int b) -> uint32_t {
+		const int i = b * kBatch + tid;
+		return (tid < kBatch && i < total) ? point_list[range.x + (uint32_t)(total - 1 - i)] : 0u;
+	};
+	auto phase1 = [&](int b, uint32_t id) {
+		const int base = b * kBatch;
+		uint32_t mask = 0;
+		if (tid < kBatch) {
+			if (base + tid < total) {
+				const float *src = rec + (size_t)id * GSR_REC_FLOATS;
+				const float2 cxy = __ldg(reinterpret_cast<const float2 *>(src));
+				const float2 ext = __ldg(reinterpret_cast<const float2 *>(src + 8));
+				mask = warp_overlap_mask(cxy.x, cxy.y, ext.x, ext.y, (float)tile_x0, (float)tile_y0);
+				// per-warp: positions at or behind the warp's deepest last contributor cannot contribute
+				const int pos = total - 1 - (base + tid);
+#pragma unroll
+				for (int w = 0; w < kWarpsPerTile; w++)
+					if (pos >= s_red[w]) mask &= ~(1u << w);
+				s_ids[(b % kIdStages) * kBatch + tid] = id;
+			}
+			s_mask[(b % kIdStages) * kBatch + tid] = (uint8_t)mask;
+		}
+	};
+
+	uint32_t next_id = load_id(0);
+	phase1(0, next_id);
+	__syncthreads();
+	stage_issue<C, kBulk>(&s_bar[0], stage_rec(0), stage_feat(0), s_ids, next_id, min(kBatch, total), rec, features, tid);
+	next_id = load_id(1);
 
 	for (int r = 0; r < rounds; r++) {
-		__syncthreads(); // previous batch fully consumed
+		if (r + 1 < rounds) phase1(r + 1, next_id);
+		stage_wait<kBulk>(&s_bar[r & 1], r >> 1);
+		__syncthreads(); // batch r landed, ids of batch r+1 visible, previous batch fully consumed
+		if (r + 1 < rounds)
+			stage_issue<C, kBulk>(&s_bar[(r + 1) & 1], stage_rec((r + 1) & 1), stage_feat((r + 1) & 1), s_ids + ((r + 1) % kIdStages) * kBatch, next_id,
+			               min(kBatch, total - (r + 1) * kBatch), rec, features, tid);
+		next_id = load_id(r + 2);
+
 		const int base = r * kBatch;
 		const int count = min(kBatch, total - base);
-		if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)count * TR::kBytesPerGaussian);
-		uint32_t mask = 0;
-		if (tid < count) {
-			const uint32_t id = next_id;
-			s_ids[tid] = id;
-			const float *src = rec + (size_t)id * GSR_REC_FLOATS;
-			bulk_g2s(s_rec + tid * GSR_REC_FLOATS, src, GSR_REC_BYTES, &s_bar);
-			if (!TR::kFeatInRec) bulk_g2s(s_feat + tid * C, features + (size_t)id * C, C * 4, &s_bar);
-			const float2 cxy = __ldg(reinterpret_cast<const float2 *>(src));
-			const float2 ext = __ldg(reinterpret_cast<const float2 *>(src + 8));
-			mask = warp_overlap_mask(cxy.x, cxy.y, ext.x, ext.y, (float)tile_x0, (float)tile_y0);
-			// per-warp: positions at or behind the warp's deepest last contributor cannot contribute
-			const int pos = total - 1 - (base + tid);
-#pragma unroll
-			for (int w = 0; w < kWarpsPerTile; w++)
-				if (pos >= s_red[w]) mask &= ~(1u << w);
-		}
-		s_mask[tid] = (uint8_t)mask;
-		{
-			const int nb = base + kBatch + tid;
-			next_id = (nb < total) ? point_list[range.x + (uint32_t)(total - 1 - nb)] : 0u;
-		}
-		__syncthreads();
+		const float *s_rec = stage_rec(r & 1);
+		const float *s_feat = stage_feat(r & 1);
+		const uint32_t *ids = s_ids + (r % kIdStages) * kBatch;
 		uint8_t *my_list = s_list + warp * kBatch;
-		const int n = build_warp_list(s_mask, my_list, warp, lane, count);
-		mbar_wait(&s_bar, (uint32_t)(r & 1));
+		const int n = build_warp_list(s_mask + (r % kIdStages) * kBatch, my_list, warp, lane, count);
 
 		for (int k = 0; k < n; k++) {
 			const int j = my_list[k];
@@ -201,9 +225,17 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 			const float4 r1 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 4); // c o depth unc
 			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
 			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
+			// cheap necessary condition first: alpha = min(.99, o*exp(power)) >= 1/255 needs power >= -log(255 o) - eps
+			// (r[14], written by preprocess with a safety margin); most culled-in-vain iterations stop here, before exp
+#if GSR_BWD_EARLYVOTE
+			const bool maybe = (pos < last_contributor) && !(power > 0.0f) && (power >= s_rec[j * GSR_REC_FLOATS + 14]);
+			if (!__any_sync(0xffffffffu, maybe)) continue;
+#else
+			const bool maybe = (pos < last_contributor) && !(power > 0.0f);
+#endif
 			const float G = expf(power);
 			const float alpha = min(0.99f, __fmul_rn(r1.y, G));
-			const bool valid = (pos < last_contributor) && !(power > 0.0f) && !(alpha < kAlphaMin);
+			const bool valid = maybe && !(alpha < kAlphaMin);
 			if (!__any_sync(0xffffffffu, valid)) continue;
 
 			float v[NV];
@@ -211,32 +243,55 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 			for (int i = 0; i < NV; i++) v[i] = 0.f;
 			float w = 0.f;
 			if (valid) {
-				T = __fdiv_rn(T, __fsub_rn(1.f, alpha));
+				// T <- T / (1 - alpha) (CR/backward.cu:533), as T * rcp(1 - alpha); the reciprocal also serves the
+				// background term
+#if GSR_BWD_RCP
+				const float rinv = __frcp_rn(__fsub_rn(1.f, alpha));
+				T = T * rinv;
+#else
+				const float one_minus = __fsub_rn(1.f, alpha);
+				T = __fdiv_rn(T, one_minus);
+#endif
 				w = alpha * T;
-				// dot = f_j . g_p over colour channels, depth and uncertainty
-				float dot = r1.z * gd + r1.w * gu;
+				// dot = f_j . g_p over colour channels, depth and uncertainty; four independent partial sums so the
+				// FMA latency chain is 1/4 as long
+#if GSR_BWD_ACC4
+				float d0 = r1.z * gd, d1 = r1.w * gu, d2 = 0.f, d3 = 0.f;
+#else
+				float d0 = r1.z * gd + r1.w * gu;
+				float &d1 = d0, &d2 = d0, &d3 = d0;
+#endif
 				if (TR::kFeatInRec) {
 					const float4 r2 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 8);
 					const float cb = s_rec[j * GSR_REC_FLOATS + 12];
-					if (C > 0) dot += r2.z * g[0];
-					if (C > 1) dot += r2.w * g[1 % C];
-					if (C > 2) dot += cb * g[2 % C];
+					if (C > 0) d2 += r2.z * g[0];
+					if (C > 1) d3 += r2.w * g[1 % C];
+					if (C > 2) d0 += cb * g[2 % C];
 				} else {
 					const float4 *f4 = reinterpret_cast<const float4 *>(s_feat + j * C);
 #pragma unroll
 					for (int q = 0; q < C / 4; q++) {
 						const float4 f = f4[q];
-						dot += f.x * g[4 * q + 0];
-						dot += f.y * g[4 * q + 1];
-						dot += f.z * g[4 * q + 2];
-						dot += f.w * g[4 * q + 3];
+						d0 += f.x * g[4 * q + 0];
+						d1 += f.y * g[4 * q + 1];
+						d2 += f.z * g[4 * q + 2];
+						d3 += f.w * g[4 * q + 3];
 					}
 				}
+#if GSR_BWD_ACC4
+				const float dot = (d0 + d1) + (d2 + d3);
+#else
+				const float dot = d0;
+#endif
 				X = last_alpha * last_dot + (1.f - last_alpha) * X;
 				last_dot = dot;
 				float dL_dalpha = (dot - X) * T;
 				last_alpha = alpha;
-				dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+#if GSR_BWD_RCP
+				dL_dalpha += neg_Tfinal_bg * rinv;
+#else
+				if (bg_dot != 0.f) dL_dalpha += (-T_final / one_minus) * bg_dot;
+#endif
 
 				const float dL_dG = r1.y * dL_dalpha;
 				const float gdx = G * d.x, gdy = G * d.y;
@@ -255,7 +310,7 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 					for (int ch = 0; ch < C; ch++) v[8 + ch] = w * g[ch];
 				}
 			}
-			const uint32_t id = s_ids[j];
+			const uint32_t id = ids[j];
 
 			warp_transpose_reduce<NV>(v, lane);
 			if (vowner<NV>(lane)) {
@@ -266,21 +321,31 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(
 			if (kLaneChannel) {
 				s_w[warp][lane] = w;
 				__syncwarp();
-				float sum = 0.f;
+#if GSR_BWD_ACC4
+				float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#else
+				float s0 = 0.f;
+				float &s1 = s0, &s2 = s0, &s3 = s0;
+#endif
 				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[warp]);
 #pragma unroll
 				for (int q = 0; q < 8; q++) {
 					const float4 ww = w4[q];
-					sum += ww.x * gcol[4 * q + 0];
-					sum += ww.y * gcol[4 * q + 1];
-					sum += ww.z * gcol[4 * q + 2];
-					sum += ww.w * gcol[4 * q + 3];
+					s0 += ww.x * gcol[4 * q + 0];
+					s1 += ww.y * gcol[4 * q + 1];
+					s2 += ww.z * gcol[4 * q + 2];
+					s3 += ww.w * gcol[4 * q + 3];
 				}
-				red_add(dL_dcolors + (size_t)id * C + lane, sum); // 32 lanes -> one coalesced 128-B RED
+#if GSR_BWD_ACC4
+				red_add(dL_dcolors + (size_t)id * C + lane, (s0 + s1) + (s2 + s3)); // 32 lanes -> one coalesced 128-B RED
+#else
+				red_add(dL_dcolors + (size_t)id * C + lane, s0);
+#endif
 				__syncwarp();
 			}
 		}
 	}
+	stage_drain<kBulk>();
 }
 
 template <int C>

@@ -10,14 +10,16 @@
 //   uncertainty do not.
 // What is different (B200-first):
 //   * the tile's slab (64-B projected records, plus a C*4-B feature row for C > 3) is gathered into
-//     shared memory by per-Gaussian bulk-async copies (cp.async.bulk -> SASS UBLKCP, the non-tensor TMA
-//     path) completing on an mbarrier — no register staging, features included (the reference re-reads
-//     colour and depth from global memory for every contributing pixel, forward.cu:545-546);
+//     shared memory asynchronously (16-B cp.async chunks, double-buffered, one barrier per 128-Gaussian
+//     round) — no register staging, features included (the reference re-reads colour and depth from global
+//     memory for every contributing pixel, forward.cu:545-546).  Round 1 first used per-Gaussian bulk copies
+//     (cp.async.bulk / UBLKCP + mbarrier); ncu showed their uniform-register operands serialise a warp's 32
+//     gathers into 32 issue rounds (13 % of this kernel's instructions), see profiles/ and DESIGN.md;
 //   * each warp owns an 8x4 pixel block and first compacts the staged batch down to the Gaussians whose
 //     alpha >= 1/255 bounding box touches its block (conservative, computed in preprocess), so the
 //     per-pair work is only spent where a contribution is possible.  The skipped pairs are exactly pairs
 //     the reference `continue`s over, so results and n_contrib are unchanged;
-//   * Gaussian ids for the next batch are prefetched while the current one is blended.
+//   * Gaussian ids two batches ahead and slabs one batch ahead are in flight while the current one is blended.
 #include "gsr_blend.cuh"
 
 namespace gsr {
@@ -30,15 +32,18 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
     float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_unc)
 {
 	using TR = BlendTraits<C>;
+	constexpr bool kBulk = GSR_FWD_BULK != 0;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	float *s_rec = reinterpret_cast<float *>(smem_raw);                                   // [256][16]
-	float *s_feat = reinterpret_cast<float *>(smem_raw + (size_t)kBatch * GSR_REC_BYTES); // [256][C]
-	uint8_t *s_list = smem_raw + TR::kStageBytes;                                         // [8][256]
-	uint8_t *s_mask = s_list + kWarpsPerTile * kBatch;                                    // [256]
-	__shared__ __align__(8) uint64_t s_bar;
+	uint32_t *s_ids = reinterpret_cast<uint32_t *>(smem_raw + TR::kIdsOff);  // [3][kBatch]
+	uint8_t *s_mask = smem_raw + TR::kMaskOff;                               // [3][kBatch]
+	uint8_t *s_list = smem_raw + TR::kListOff;                               // [8][kBatch]
+	auto stage_rec = [&](int s) { return reinterpret_cast<float *>(smem_raw + (size_t)s * TR::kStageBytes); };
+	auto stage_feat = [&](int s) { return reinterpret_cast<float *>(smem_raw + (size_t)s * TR::kStageBytes + (size_t)kBatch * GSR_REC_BYTES); };
 
+	__shared__ __align__(8) uint64_t s_bar[kStages];
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int tile = blockIdx.x;
+	stage_init<C, kBulk>(s_bar, tid);
 	const int tile_x0 = (tile % tiles_x) * GSR_BLOCK_X, tile_y0 = (tile / tiles_x) * GSR_BLOCK_Y;
 	int bx, by;
 	warp_block_origin(warp, bx, by);
@@ -50,11 +55,6 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
 	const int total = (int)(range.y - range.x);
 	const int rounds = (total + kBatch - 1) / kBatch;
 
-	if (tid == 0) {
-		mbar_init(&s_bar, 1);
-		mbar_fence_init();
-	}
-
 	float T = 1.0f;
 	uint32_t last_contributor = 0;
 	float acc[C];
@@ -63,42 +63,60 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
 	float D = 0.f, UNC = 0.f;
 	bool done = !inside;
 
-	uint32_t next_id = (tid < total) ? point_list[range.x + tid] : 0u;
-	__syncthreads(); // barrier init visible
+	// Staging, per batch b of kBatch list entries (threads < kBatch own one entry each):
+	//   phase 1: id -> s_ids[b%3]; bounding extents from L2 -> per-warp overlap mask -> s_mask[b%3]
+	//   phase 2 (all threads, after a barrier): 16-B cp.async chunks of the records / feature rows -> stage b%2
+	auto phase1 = [&](int b, uint32_t id) {
+		const int base = b * kBatch;
+		uint32_t mask = 0;
+		if (tid < kBatch) {
+			if (base + tid < total) {
+				const float *src = rec + (size_t)id * GSR_REC_FLOATS;
+				const float2 cxy = __ldg(reinterpret_cast<const float2 *>(src));
+				const float2 ext = __ldg(reinterpret_cast<const float2 *>(src + 8));
+				mask = warp_overlap_mask(cxy.x, cxy.y, ext.x, ext.y, (float)tile_x0, (float)tile_y0);
+				s_ids[(b % kIdStages) * kBatch + tid] = id;
+			}
+			s_mask[(b % kIdStages) * kBatch + tid] = (uint8_t)mask;
+		}
+	};
+	auto load_id = [&](int b) -> uint32_t {
+		const int i = b * kBatch + tid;
+		return (tid < kBatch && i < total) ? point_list[range.x + i] : 0u;
+	};
+
+	// prologue: batch 0 fully issued, id of batch 1 in flight
+	uint32_t next_id = load_id(0);
+	if (rounds > 0) {
+		phase1(0, next_id);
+		__syncthreads();
+		stage_issue<C, kBulk>(&s_bar[0], stage_rec(0), stage_feat(0), s_ids, next_id, min(kBatch, total), rec, features, tid);
+	}
+	next_id = load_id(1);
 
 	for (int r = 0; r < rounds; r++) {
-		// whole tile finished? (CR/forward.cu:496-498)
-		if (__syncthreads_count(done) == 256) break; // also: everyone is past the previous batch's smem reads
+		if (r + 1 < rounds) phase1(r + 1, next_id);
+		stage_wait<kBulk>(&s_bar[r & 1], r >> 1);
+		// one barrier per round: batch r has landed for everyone, ids of batch r+1 are visible, and every warp
+		// is past the previous batch's reads.  It doubles as the whole-tile early exit (CR/forward.cu:496-498).
+		if (__syncthreads_count(done) == 256) break;
+		if (r + 1 < rounds)
+			stage_issue<C, kBulk>(&s_bar[(r + 1) & 1], stage_rec((r + 1) & 1), stage_feat((r + 1) & 1), s_ids + ((r + 1) % kIdStages) * kBatch, next_id,
+			               min(kBatch, total - (r + 1) * kBatch), rec, features, tid);
+		next_id = load_id(r + 2);
+
 		const int base = r * kBatch;
 		const int count = min(kBatch, total - base);
-
-		// ---- stage this batch: one bulk-async gather per Gaussian, issued by its thread ----
-		if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)count * TR::kBytesPerGaussian);
-		uint32_t mask = 0;
-		if (tid < count) {
-			const uint32_t id = next_id;
-			const float *src = rec + (size_t)id * GSR_REC_FLOATS;
-			bulk_g2s(s_rec + tid * GSR_REC_FLOATS, src, GSR_REC_BYTES, &s_bar);
-			if (!TR::kFeatInRec) bulk_g2s(s_feat + tid * C, features + (size_t)id * C, C * 4, &s_bar);
-			// bounding extents straight from L2 (one 8-B + one 8-B load; conflict-free, unlike a strided smem read)
-			const float2 cxy = __ldg(reinterpret_cast<const float2 *>(src));
-			const float2 ext = __ldg(reinterpret_cast<const float2 *>(src + 8));
-			mask = warp_overlap_mask(cxy.x, cxy.y, ext.x, ext.y, (float)tile_x0, (float)tile_y0);
-		}
-		s_mask[tid] = (uint8_t)mask;
-		// prefetch the ids of the next batch
-		next_id = (base + kBatch + tid < total) ? point_list[range.x + base + kBatch + tid] : 0u;
-		__syncthreads(); // masks visible
+		const float *s_rec = stage_rec(r & 1);
+		const float *s_feat = stage_feat(r & 1);
 		uint8_t *my_list = s_list + warp * kBatch;
-		const int n = build_warp_list(s_mask, my_list, warp, lane, count);
-		mbar_wait(&s_bar, (uint32_t)(r & 1)); // slab has landed
-
 		if (__all_sync(0xffffffffu, done)) continue;
+		const int n = build_warp_list(s_mask + (r % kIdStages) * kBatch, my_list, warp, lane, count);
+
 		for (int k = 0; k < n; k++) {
 			const int j = my_list[k];
 			const float4 r0 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS);     // x y a b
 			const float4 r1 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 4); // c o depth unc
-			// same expression as CR/forward.cu:521-525
 			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
 			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
 			if (done || power > 0.0f) continue;
@@ -133,6 +151,7 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
 			last_contributor = (uint32_t)(base + j + 1);
 		}
 	}
+	stage_drain<kBulk>(); // nothing may be in flight into shared memory when the CTA retires
 
 	if (inside) {
 		const size_t pix_id = (size_t)W * py + px;

@@ -16,7 +16,8 @@
 // by the blend kernels.  16 floats = 64 B so that one cp.async.bulk moves one Gaussian.
 //   [0] x  [1] y  [2] conic.a  [3] conic.b | [4] conic.c  [5] opacity  [6] depth  [7] uncertainty
 //   [8] hx [9] hy (half extents of the alpha >= 1/255 ellipse's bounding box, conservative)
-//   [10..12] rgb (only when C <= 3: colours ride in the record)   [13] radius (integral)  [14..15] spare
+//   [10..12] rgb (only when C <= 3: colours ride in the record)   [13] radius (integral)
+//   [14] pow_min: lower bound on `power` below which alpha < 1/255 for sure  [15] spare
 #define GSR_REC_FLOATS 16
 #define GSR_REC_BYTES 64
 

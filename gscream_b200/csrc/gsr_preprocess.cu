@@ -316,11 +316,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 					// sqrt(tau * (Q^-1)_xx) = sqrt(tau * c / (ac - b^2)); evaluated in double from the
 					// rounded conic so that cancellation in (ac - b^2) cannot make the box too small.
 					float hx = -1.f, hy = -1.f; // negative: nothing can contribute
+					float pow_min = __int_as_float(0xff800000); // -inf: "power >= pow_min" never culls
 					if (!(opacity == opacity)) { // NaN opacity: never cull
 						hx = hy = __int_as_float(0x7f800000);
 					} else if (opacity >= 1.0f / 255.0f) {
 						const double qa = conic.x, qb = conic.y, qc = conic.z;
 						const double dq = qa * qc - qb * qb;
+						// necessary condition for alpha >= 1/255: power >= -log(255 opacity), with slack
+						pow_min = __double2float_rd(-(log(255.0 * (double)opacity) * 1.0005 + 0.005));
 						if (dq > 0.0 && qa > 0.0 && qc > 0.0) {
 							const double tau = 2.0 * log(255.0 * (double)opacity) * 1.001 + 0.02;
 							hx = __double2float_ru(sqrt(tau * qc / dq) * 1.0005 + 0.02);
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 					r4[0] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
 					r4[1] = make_float4(conic.z, opacity, p_view.z, unc);
 					r4[2] = make_float4(hx, hy, cr, cg);
-					r4[3] = make_float4(cb, my_radius, 0.f, 0.f); // radius (exact in fp32) for the instance emission
+					r4[3] = make_float4(cb, my_radius, pow_min, 0.f); // [13] radius (exact in fp32) for the instance emission
 				}
 			}
 		}
