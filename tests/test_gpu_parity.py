@@ -223,6 +223,64 @@ def test_filters_and_mark_visible_match_forward_and_oracle():
     assert torch.equal(rast.visible_filter(means3D=s["means3D"], scales=wide[:, :3], rotations=s["rotations"]), radii)
 
 
+@pytest.mark.parametrize("degree", [0, 1, 2, 3])
+def test_spherical_harmonics_path_matches_reference_build(degree):
+    """shs instead of colors_precomp (C = 3 only, CR/forward.cu:22-73 / CR/backward.cu:20-139).  GScream never takes this
+    path (shs=None, gaussian_renderer/__init__.py:152) but it is part of the drop-in surface; the oracle does not restate
+    it, so the reference's own build is the checker."""
+    _require_native()
+    if not ru.ref_available(3):
+        pytest.skip("oracle/_ref/dgr3 not built")
+    ref_mod = ru.load_ref(3)
+    dev = torch.device("cuda")
+    P, W, H = 3000, 200, 120
+    sc = scenes.make_scene(P, W, H, 3, 401, scale_mult=2.0, bg_value=0.1)
+    cam = scenes.make_camera(W, H, yaw_deg=4.0)
+    # camera away from the origin so that view directions vary
+    gen = torch.Generator().manual_seed(5)
+    shs_cpu = (torch.randn(P, 16, 3, generator=gen) * 0.4)
+    grads = scenes.make_upstream_grads(3, W, H, 401)
+    res = {}
+    for name, mod in (("ref", ref_mod), ("ours", ours)):
+        s = {k: v.to(dev) for k, v in sc.items()}
+        shs = shs_cpu.to(dev).requires_grad_(True)
+        means = s["means3D"].clone().requires_grad_(True)
+        st = mod.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=s["bg"],
+                                               scale_modifier=1.0, viewmatrix=cam["viewmatrix"].to(dev), projmatrix=cam["projmatrix"].to(dev),
+                                               sh_degree=degree, campos=torch.tensor([0.3, -0.2, -1.0], device=dev), prefiltered=False, debug=False)
+        rast = mod.GaussianRasterizer(raster_settings=st)
+        color, depth, unc, radii = rast(means3D=means, means2D=torch.zeros(P, 3, device=dev, requires_grad=True), opacities=s["opacities"],
+                                        uncertainties=s["uncertainties"], shs=shs, colors_precomp=None, scales=s["scales"], rotations=s["rotations"],
+                                        cov3D_precomp=None)
+        torch.autograd.backward((color, depth, unc), tuple(g.to(dev) for g in grads))
+        res[name] = dict(color=color.detach().cpu().numpy(), radii=radii.cpu().numpy(), dsh=shs.grad.cpu().numpy(), dmeans=means.grad.cpu().numpy())
+    assert np.array_equal(res["ours"]["radii"], res["ref"]["radii"])
+    for k, rel in (("color", REL), ("dsh", 3 * REL), ("dmeans", 1e-4)):
+        ref = res["ref"][k]
+        assert np.abs(res["ours"][k] - ref).max() <= rel * np.abs(ref).max() + 1e-12, (k, float(np.abs(res["ours"][k] - ref).max()), float(np.abs(ref).max()))
+
+
+def test_debug_mode_and_repeated_backward():
+    """debug=True synchronises after each stage (auxiliary.h:166-173); train.py calls backward(retain_graph=True)."""
+    _require_native()
+    dev = torch.device("cuda")
+    P, W, H, C = 1500, 96, 64, 3
+    s = {k: v.to(dev) for k, v in scenes.make_scene(P, W, H, C, 77, scale_mult=2.0).items()}
+    cam = scenes.make_camera(W, H)
+    st = ours.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], s["bg"], 1.0, cam["viewmatrix"].to(dev),
+                                            cam["projmatrix"].to(dev), 1, cam["campos"].to(dev), False, True)
+    means = s["means3D"].clone().requires_grad_(True)
+    color, depth, unc, radii = ours.GaussianRasterizer(st)(means3D=means, means2D=torch.zeros(P, 3, device=dev), opacities=s["opacities"],
+                                                           uncertainties=s["uncertainties"], colors_precomp=s["colors"], scales=s["scales"],
+                                                           rotations=s["rotations"])
+    loss = color.mean() + depth.mean()
+    loss.backward(retain_graph=True)
+    g1 = means.grad.clone()
+    means.grad = None
+    loss.backward()
+    assert torch.allclose(means.grad, g1, rtol=1e-4, atol=1e-9)
+
+
 # ---- (3) the reference's own CUDA build at BASELINE.json's full sizes ------------------------------------------
 @pytest.mark.parametrize("cfg", ["config2", "config3"])
 def test_full_size_against_reference_build(cfg):
