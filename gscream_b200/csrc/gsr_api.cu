@@ -70,6 +70,7 @@ cudaError_t launch_preprocess_backward(const PreBwdArgs &a, cudaStream_t stream)
 cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStream_t stream);
 cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const GeomLayout &GL, char *binning,
                           const BinningLayout &BL, char *image, const ImageLayout &IL, cudaStream_t stream);
+int point_list_index(int W, int H);
 cudaError_t launch_blend_forward(int C, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
                                  const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
                                  float *out_depth, float *out_unc, cudaStream_t stream);
@@ -200,7 +201,7 @@ int gsr_forward_stage2(int P, int C, int64_t num_rendered, const float *colors_p
 	{ StageTimer t(kBin, stream); GSR_CUDA(bin_instances(P, num_rendered, width, height, geom, GL, binning, BL, image, IL, stream)); }
 	{
 		StageTimer t(kBlendFwd, stream);
-		GSR_CUDA(launch_blend_forward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[1]),
+		GSR_CUDA(launch_blend_forward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
 		                              (const float *)(geom + GL.rec), colors_precomp, background, (float *)(image + IL.final_T),
 		                              (uint32_t *)(image + IL.n_contrib), out_color, out_depth, out_uncertainty, stream));
 	}
@@ -241,7 +242,7 @@ int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const
 	count_launch(2);
 	if (num_rendered > 0) {
 		StageTimer t(kBlendBwd, stream);
-		GSR_CUDA(launch_blend_backward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[1]),
+		GSR_CUDA(launch_blend_backward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
 		                               (const float *)(geom + GL.rec), colors_precomp, background, (const float *)(image + IL.final_T),
 		                               (const uint32_t *)(image + IL.n_contrib), dL_dout_color, dL_dout_depth, dL_dout_uncertainty, gacc,
 		                               dL_dcolors, stream));
@@ -359,7 +360,7 @@ int gsr_debug_export(int P, int64_t num_rendered, int width, int height, const v
 	}
 	if (geom && tiles_touched) GSR_CUDA(cudaMemcpyAsync(tiles_touched, geom + GL.tiles_touched, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream));
 	if (binning && point_list && num_rendered > 0)
-		GSR_CUDA(cudaMemcpyAsync(point_list, binning + BL.val[1], (size_t)num_rendered * 4, cudaMemcpyDeviceToDevice, stream));
+		GSR_CUDA(cudaMemcpyAsync(point_list, binning + BL.val[point_list_index(width, height)], (size_t)num_rendered * 4, cudaMemcpyDeviceToDevice, stream));
 	if (image && ranges) GSR_CUDA(cudaMemcpyAsync(ranges, image + IL.ranges, tiles * 8, cudaMemcpyDeviceToDevice, stream));
 	if (image && final_T) GSR_CUDA(cudaMemcpyAsync(final_T, image + IL.final_T, N * 4, cudaMemcpyDeviceToDevice, stream));
 	if (image && n_contrib) GSR_CUDA(cudaMemcpyAsync(n_contrib, image + IL.n_contrib, N * 4, cudaMemcpyDeviceToDevice, stream));

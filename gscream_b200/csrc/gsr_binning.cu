@@ -18,14 +18,29 @@
 // Gaussian index) as well.  Depth keys are positive floats (z > 0.2), so their bit patterns order like
 // the values (CR/rasterizer_impl.cu:102-106).
 //
-// The radix-sort / scan primitives are CUB's for now (stop-gap, as allowed by SURVEY.md section 7);
-// everything around them is hand-written.
+// The stable radix sort and the prefix sum are hand-written (gsr_sort.cu).  Building with -DGSR_USE_CUB=1 swaps
+// in cub::DeviceRadixSort / cub::DeviceScan for A/B timing (profiles/r1_sort_ab.md); results are identical.
 #include "gsr_common.cuh"
+#include "gsr_sort.cuh"
+#include <algorithm>
+#ifndef GSR_USE_CUB
+#define GSR_USE_CUB 0
+#endif
+#if GSR_USE_CUB
 #include <cub/cub.cuh>
+#endif
 
 namespace gsr {
 
 // -------- scratch layouts ---------------------------------------------------------------------
+static int tile_bits(int W, int H)
+{
+	const int tiles = ((W + GSR_BLOCK_X - 1) / GSR_BLOCK_X) * ((H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y);
+	int bits = 1;
+	while ((1 << bits) < tiles) bits++;
+	return bits;
+}
+#if GSR_USE_CUB
 static size_t sort_temp_bytes(int64_t n)
 {
 	// Out-of-place radix sort: CUB needs an alternate key and value array plus histograms / look-back
@@ -53,6 +68,28 @@ static size_t scan_temp_bytes(int n)
 	return std::max(bytes, (size_t(1) << 20));
 }
 
+#endif
+
+// Where the sorted arrays end up ([0] or [1] of the ping-pong pairs): a pure function of the problem shape, so
+// forward, backward and the debug export agree without any state.
+int depth_order_index()
+{
+#if GSR_USE_CUB
+	return 1;
+#else
+	return radix_plan(1, 32).passes & 1; // 4 passes -> back in [0]
+#endif
+}
+int point_list_index(int W, int H)
+{
+#if GSR_USE_CUB
+	(void)W; (void)H;
+	return 1;
+#else
+	return radix_plan(1, tile_bits(W, H)).passes & 1;
+#endif
+}
+
 GeomLayout geom_layout(int P)
 {
 	GeomLayout L;
@@ -69,7 +106,11 @@ GeomLayout geom_layout(int P)
 	L.gacc = take(p * 32);
 	L.clamped = take(p * 3);
 	L.rgb = take(p * 12);
+#if GSR_USE_CUB
 	L.temp_bytes = std::max(sort_temp_bytes(P), scan_temp_bytes(P));
+#else
+	L.temp_bytes = radix_plan(P, 32).bytes + scan_scratch_bytes(P);
+#endif
 	L.temp = take(L.temp_bytes);
 	L.total = off;
 	return L;
@@ -91,7 +132,7 @@ ImageLayout image_layout(int W, int H)
 
 BinningLayout binning_layout(int P, int64_t R, int W, int H)
 {
-	(void)P; (void)W; (void)H;
+	(void)P;
 	BinningLayout L;
 	size_t off = 0;
 	const size_t r = (size_t)std::max<int64_t>(R, 1);
@@ -100,7 +141,12 @@ BinningLayout binning_layout(int P, int64_t R, int W, int H)
 	L.key[1] = take(r * 4);
 	L.val[0] = take(r * 4);
 	L.val[1] = take(r * 4);
+#if GSR_USE_CUB
+	(void)W; (void)H;
 	L.temp_bytes = sort_temp_bytes(R);
+#else
+	L.temp_bytes = radix_plan(R, tile_bits(W, H)).bytes;
+#endif
 	L.temp = take(L.temp_bytes);
 	L.total = off;
 	return L;
@@ -151,15 +197,16 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint3
 }
 
 // -------- host orchestration --------------------------------------------------------------------
-// Stage-1 tail: depth order (always lands in depth_val[1]) + scan of tiles_touched in that order.
+// Stage-1 tail: stable depth order of the Gaussians + inclusive scan of tiles_touched in that order.
 // offsets[P-1] is then R (num_rendered).
 cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStream_t stream)
 {
 	if (P <= 0) return cudaSuccess;
+	cudaError_t e;
+#if GSR_USE_CUB
 	size_t temp = L.temp_bytes;
-	cudaError_t e = cub::DeviceRadixSort::SortPairs(geom + L.temp, temp, (const uint32_t *)(geom + L.depth_key[0]),
-	                                                (uint32_t *)(geom + L.depth_key[1]), (const uint32_t *)(geom + L.depth_val[0]),
-	                                                (uint32_t *)(geom + L.depth_val[1]), P, 0, 32, stream);
+	e = cub::DeviceRadixSort::SortPairs(geom + L.temp, temp, (const uint32_t *)(geom + L.depth_key[0]), (uint32_t *)(geom + L.depth_key[1]),
+	                                    (const uint32_t *)(geom + L.depth_val[0]), (uint32_t *)(geom + L.depth_val[1]), P, 0, 32, stream);
 	if (e != cudaSuccess) return e;
 	count_launch(5);
 	const uint32_t *order = (const uint32_t *)(geom + L.depth_val[1]);
@@ -170,9 +217,17 @@ cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStr
 	if (e != cudaSuccess) return e;
 	count_launch(2);
 	return cudaGetLastError();
+#else
+	const int which = radix_sort_pairs((uint32_t *)(geom + L.depth_key[0]), (uint32_t *)(geom + L.depth_val[0]), (uint32_t *)(geom + L.depth_key[1]),
+	                                   (uint32_t *)(geom + L.depth_val[1]), P, 32, geom + L.temp, stream, &e);
+	if (e != cudaSuccess) return e;
+	const uint32_t *order = (const uint32_t *)(geom + L.depth_val[which]);
+	return inclusive_sum_gather((const uint32_t *)(geom + L.tiles_touched), order, (uint32_t *)(geom + L.offsets), P,
+	                            geom + L.temp + radix_plan(P, 32).bytes, stream);
+#endif
 }
 
-// Stage-2 head: emission, per-tile bucketing (point_list always lands in val[1]), ranges.
+// Stage-2 head: emission, stable bucketing by tile id, ranges.
 cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const GeomLayout &GL,
                           char *binning, const BinningLayout &BL, char *image, const ImageLayout &IL, cudaStream_t stream)
 {
@@ -180,9 +235,10 @@ cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const Geom
 	const int tiles = gx * gy;
 	cudaError_t e = cudaMemsetAsync(image + IL.ranges, 0, (size_t)tiles * sizeof(uint2), stream); // CR/rasterizer_impl.cu:316
 	if (e != cudaSuccess) return e;
+	count_launch();
 	if (P <= 0 || R <= 0) return cudaSuccess;
 
-	const uint32_t *order = (const uint32_t *)(geom + GL.depth_val[1]);
+	const uint32_t *order = (const uint32_t *)(geom + GL.depth_val[depth_order_index()]);
 	emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order, (const uint32_t *)(geom + GL.offsets),
 	                                                         (const uint32_t *)(geom + GL.tiles_touched), (const float *)(geom + GL.rec),
 	                                                         gx, gy, (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
@@ -190,15 +246,20 @@ cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const Geom
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
 
-	int bits = 1;
-	while ((1 << bits) < tiles) bits++;
+	const int bits = tile_bits(W, H);
+#if GSR_USE_CUB
 	size_t temp = BL.temp_bytes;
 	e = cub::DeviceRadixSort::SortPairs(binning + BL.temp, temp, (const uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.key[1]),
 	                                    (const uint32_t *)(binning + BL.val[0]), (uint32_t *)(binning + BL.val[1]), (int)R, 0, bits, stream);
 	if (e != cudaSuccess) return e;
 	count_launch(1 + (bits + 7) / 8);
-
-	tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, (const uint32_t *)(binning + BL.key[1]), (uint2 *)(image + IL.ranges));
+	const int which = 1;
+#else
+	const int which = radix_sort_pairs((uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]), (uint32_t *)(binning + BL.key[1]),
+	                                   (uint32_t *)(binning + BL.val[1]), R, bits, binning + BL.temp, stream, &e);
+	if (e != cudaSuccess) return e;
+#endif
+	tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, (const uint32_t *)(binning + BL.key[which]), (uint2 *)(image + IL.ranges));
 	count_launch();
 	return cudaGetLastError();
 }
