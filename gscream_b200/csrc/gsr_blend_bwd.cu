@@ -76,8 +76,13 @@ __device__ __forceinline__ bool vowner(int lane)
 	return (lane & rest) == 0;
 }
 
+// C = 32 keeps a 34-float gradient row and a 32-float gradient column per lane: 124 registers, 2 CTAs/SM (forcing 3
+// spills 108 B and is 18 % slower, profiles/r1_occupancy_ab.md).  Small C fits 3.
+#ifndef GSR_BWD_MINBLOCKS
+#define GSR_BWD_MINBLOCKS(C) ((C) <= 8 ? 3 : 2)
+#endif
 template <int C>
-__global__ void __launch_bounds__(256) blend_backward_kernel(
+__global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kernel(
     const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,

@@ -24,8 +24,13 @@
 
 namespace gsr {
 
+// Resident CTAs per SM the register allocation must allow.  Measured (profiles/r1_occupancy_ab.md): the forward
+// kernel is latency bound, 4 CTAs/SM (64 registers, 12 B of spill at C = 32) beats 3 CTAs/SM (80 registers) by 10 %.
+#ifndef GSR_FWD_MINBLOCKS
+#define GSR_FWD_MINBLOCKS 4
+#endif
 template <int C>
-__global__ void __launch_bounds__(256) blend_forward_kernel(
+__global__ void __launch_bounds__(256, GSR_FWD_MINBLOCKS) blend_forward_kernel(
     const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
