@@ -7,6 +7,8 @@
 Bars: integer / index artefacts (radii, tiles_touched, R, point_list, ranges, n_contrib) and the fp32 projection
 (xy, depth, conic) bit-exact; rendered planes and gradients within 1e-5 of the plane's scale
 (+ the reference's measured atomic run-to-run spread for gradients)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -304,6 +306,55 @@ def test_full_size_against_reference_build(cfg):
     _check_ints_and_projection(m, e, r["radii"], geom, img, binn["point_list"], R)
     spread = {k: float(np.abs(r2[k] - r[k]).max()) for k in GRAD_KEYS}
     _check_floats(m, r, spread)
+
+
+def _compare_with_reference_build(scene, cam, grads, C):
+    ref_mod = ru.load_ref(C)
+    P, W, H = scene["means3D"].shape[0], cam["W"], cam["H"]
+    r = ru.run_impl(ref_mod, scene, cam, grads)
+    r2 = ru.run_impl(ref_mod, scene, cam, grads)
+    m = ru.run_impl(ours, scene, cam, grads)
+    R = r["num_rendered"]
+    geom = ru.parse_ref_geom(r["_geom"].cpu().numpy(), P)
+    img = ru.parse_ref_image(r["_img"].cpu().numpy(), W, H)
+    binn = ru.parse_ref_binning(r["_binning"].cpu().numpy(), R)
+    e = _export(m, P, W, H)
+    _check_ints_and_projection(m, e, r["radii"], geom, img, binn["point_list"], R)
+    spread = {k: float(np.abs(r2[k] - r[k]).max()) for k in GRAD_KEYS}
+    _check_floats(m, r, spread)
+    return r
+
+
+@pytest.mark.parametrize("C", [3, 32])
+def test_adversarial_parameters_against_reference_build(C):
+    """Stress the in-kernel culling (conservative alpha >= 1/255 extents) and the thresholds: opacities at and around
+    1/255, at 0.99 and above 1, needle-like and huge splats, splats far outside the image, un-normalised quaternions."""
+    _require_native()
+    if not ru.ref_available(C):
+        pytest.skip("oracle/_ref/dgr%d not built" % C)
+    P, W, H = 6000, 333, 190
+    g = torch.Generator().manual_seed(900 + C)
+    sc = scenes.make_scene(P, W, H, C, 900 + C, scale_mult=2.0, bg_value=0.3 if C == 3 else 0.0)
+    special = torch.tensor([1 / 255, 0.99 / 255, 1.01 / 255, 0.0039, 0.004, 0.0, 0.98, 0.99, 1.0, 1.5, 0.5, 0.25])
+    sc["opacities"] = special[torch.randint(0, len(special), (P, 1), generator=g)].contiguous()
+    sc["scales"] = torch.exp(torch.empty(P, 3).uniform_(math.log(1e-4), math.log(3.0), generator=g)).contiguous()  # needles, discs, blobs
+    sc["rotations"] = (torch.randn(P, 4, generator=g) * torch.empty(P, 1).uniform_(0.5, 2.0, generator=g)).contiguous()  # NOT normalised
+    sc["means3D"][: P // 10, :2] *= 3.0  # far outside the frustum sideways (no x/y frustum test upstream, auxiliary.h:154)
+    cam = scenes.make_camera(W, H, yaw_deg=3.0)
+    grads = scenes.make_upstream_grads(C, W, H, 900 + C)
+    _compare_with_reference_build(sc, cam, grads, C)
+
+
+def test_three_digit_passes_of_the_tile_sort():
+    """> 65536 tiles: the tile-id radix sort takes three 8-bit passes (result lands in the other ping-pong buffer)."""
+    _require_native()
+    if not ru.ref_available(3):
+        pytest.skip("oracle/_ref/dgr3 not built")
+    P, W, H, C = 4000, 4112, 4112, 3   # 257 x 257 = 66049 tiles -> 17 bits
+    sc = scenes.make_scene(P, W, H, C, 950, scale_mult=6.0)
+    cam = scenes.make_camera(W, H)
+    grads = scenes.make_upstream_grads(C, W, H, 950)
+    _compare_with_reference_build(sc, cam, grads, C)
 
 
 # ---- (4) size-independent properties at full size --------------------------------------------------------------
