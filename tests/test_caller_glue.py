@@ -46,17 +46,27 @@ def test_caller_glue_same_results_with_reference_build():
     cam = scenes.make_camera(W, H)
     bg = torch.zeros(3, device=dev)
     target = torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)).to(dev)
+    # ONE anchor model and ONE decode graph feed both rasterizers, so both see bit-identical Gaussians (two separate
+    # decodes may differ in the last bit: cuBLAS picks its algorithm per call).
+    pc = ad.SyntheticAnchors(20000, seed=11, tanfov=(cam["tanfovx"], cam["tanfovy"])).to(dev)
+    params = dict(g_feat=pc._anchor_feat, g_off=pc._offset, g_anchor=pc._anchor, g_scaling=pc._scaling, g_w=pc.mlp_cov[2].weight)
     res = {}
+    filt = {name: ad.prefilter_position2D(mod, cam, pc, bg) for name, mod in (("ref", ref), ("ours", ours))}
+    vis = filt["ref"][0]
+    dec = ad.generate_neural_gaussians(cam["campos"].to(dev), pc, vis)
+    xyz, color, opacity, uncertainty, scaling, rot = dec[:6]
     for name, mod in (("ref", ref), ("ours", ours)):
-        pc = ad.SyntheticAnchors(20000, seed=11, tanfov=(cam["tanfovx"], cam["tanfovy"])).to(dev)
-        vis, x, y = ad.prefilter_position2D(mod, cam, pc, bg)
-        pkg = ad.render(mod, cam, pc, bg, vis)
-        loss = (pkg["render"] - target).abs().mean() + 0.1 * pkg["render_depth"].mean() + 0.05 * pkg["uncertainty"].mean()
-        loss.backward()
-        res[name] = dict(vis=vis.cpu().numpy(), x=x.cpu().numpy(), y=y.cpu().numpy(), image=pkg["render"].detach().cpu().numpy(),
-                         radii=pkg["radii"].cpu().numpy(), vsp=pkg["viewspace_points"].grad.cpu().numpy(), loss=float(loss),
-                         g_feat=pc._anchor_feat.grad.cpu().numpy(), g_off=pc._offset.grad.cpu().numpy(), g_anchor=pc._anchor.grad.cpu().numpy(),
-                         g_scaling=pc._scaling.grad.cpu().numpy(), g_w=pc.mlp_cov[2].weight.grad.cpu().numpy())
+        ssp = torch.zeros_like(xyz, requires_grad=True)
+        rast = mod.GaussianRasterizer(raster_settings=ad.make_settings(mod, cam, bg, dev))
+        image, depth, uncer, radii = rast(means3D=xyz, means2D=ssp, shs=None, colors_precomp=color, opacities=opacity,
+                                          uncertainties=uncertainty, scales=scaling, rotations=rot, cov3D_precomp=None)
+        loss = (image - target).abs().mean() + 0.1 * depth.mean() + 0.05 * uncer.mean()
+        for t in params.values():
+            t.grad = None
+        loss.backward(retain_graph=True)
+        res[name] = dict(vis=filt[name][0].cpu().numpy(), x=filt[name][1].cpu().numpy(), y=filt[name][2].cpu().numpy(),
+                         image=image.detach().cpu().numpy(), radii=radii.cpu().numpy(), vsp=ssp.grad.cpu().numpy(), loss=float(loss.detach()),
+                         **{k: t.grad.detach().cpu().numpy().copy() for k, t in params.items()})
     r, m = res["ref"], res["ours"]
     assert np.array_equal(m["vis"], r["vis"]) and np.array_equal(m["x"], r["x"]) and np.array_equal(m["y"], r["y"])  # prefilter: bit-exact
     assert np.array_equal(m["radii"], r["radii"])
