@@ -156,7 +156,7 @@ def run_ours(args, cfg, rank, world, local):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     P, W, H, C, seed = cfg["P"], cfg["W"], cfg["H"], cfg["C"], cfg["seed"]
-    scene_cpu = scenes.make_scene(P, W, H, C, seed)                       # identical bits on every rank
+    scene_cpu = scenes.make_scene(P, W, H, C, seed, scale_mult=args.scale_mult)  # identical bits on every rank
     yaw = (rank - (world - 1) / 2.0) * 3.0                                # every rank renders its own view
     cam_cpu = scenes.make_camera(W, H, yaw_deg=yaw)
     grads_cpu = scenes.make_upstream_grads(C, W, H, seed + rank)
@@ -252,6 +252,18 @@ def run_ours(args, cfg, rank, world, local):
     torch.cuda.synchronize()
     e2e_value = world * 1000.0 * args.steps / e2e_ms
 
+    # per-tile list length statistics (outside any timed region)
+    from gscream_b200 import _C as gC
+    outs = render_views_into_bucket(scene, [cam], ups, bucket.zero_(), keep_outputs=False)
+    R_, col_, dep_, unc_, rad_, geom_, binning_, img_ = gC.rasterize_gaussians(
+        scene["bg"], scene["means3D"], scene["colors"], scene["opacities"], scene["uncertainties"], scene["scales"], scene["rotations"], 1.0,
+        torch.empty(0), cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], H, W, torch.empty(0), 1, cam["campos"], False, False)
+    rng = gC.debug_export(P, R_, W, H, geom_, binning_, img_)["ranges"].cpu().numpy().astype(np.int64)
+    lens = rng[:, 1] - rng[:, 0]
+    tile_stats = {"mean": float(lens.mean()), "p50": float(np.percentile(lens, 50)), "p90": float(np.percentile(lens, 90)),
+                  "p99": float(np.percentile(lens, 99)), "max": int(lens.max())}
+    del R_, col_, dep_, unc_, rad_, geom_, binning_, img_, outs
+
     out = None
     if rank == 0:
         peak, peak_src = _peaks()
@@ -262,8 +274,10 @@ def run_ours(args, cfg, rank, world, local):
             "metric": "fwd+bwd views/sec", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded Gaussian cloud, SURVEY.md 8d; one camera view per GPU)",
-            "config": {"workload": "%s: %d Gaussians, %dx%d, %d feature channels + depth + uncertainty, fwd+bwd" % (args.workload, P, W, H, C),
-                       "views_per_step": world, "num_rendered": R, "visible": V, "parallelism": "view-parallel dp%d" % world,
+            "config": {"workload": "%s%s: %d Gaussians, %dx%d, %d feature channels + depth + uncertainty, fwd+bwd" % (
+                           args.workload, "" if args.scale_mult == 1.0 else " heavy (splat scale x%g)" % args.scale_mult, P, W, H, C),
+                       "views_per_step": world, "num_rendered": R, "visible": V, "instances_per_gaussian": R / max(P, 1),
+                       "tile_list_len": tile_stats, "parallelism": "view-parallel dp%d" % world,
                        "l2": "working set (features 128 MB + records 64 MB + planes 282 MB x2) exceeds the 126 MB L2; no explicit flush",
                        "collective": "1 NCCL sum-allreduce of the %.0f MB gradient bucket per step" % (bucket.nbytes() / 1e6) if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
@@ -274,7 +288,7 @@ def run_ours(args, cfg, rank, world, local):
                          "frac": (achieved / peak) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of this
                          # workload (profiles/r1_blend_v3_summary.md: 406.0 MB + 27.4 MB); config3 only
-                         "traffic": 433429248 if (args.workload == "config3") else None,
+                         "traffic": 433429248 if (args.workload == "config3" and args.scale_mult == 1.0) else None,
                          "algorithmic_bytes_per_launch": bytes_bwd,
                          "avg_launch_ms": t_bwd, "peak_source": peak_src,
                          "note": "blend kernels are FP32-issue bound, not HBM bound (see DESIGN.md / profiles/)"},
@@ -296,7 +310,7 @@ def run_reference(args, cfg, rank, world, local):
     ref = ru.load_ref(C)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    scene = {k: v.to(dev) for k, v in scenes.make_scene(P, W, H, C, seed).items()}
+    scene = {k: v.to(dev) for k, v in scenes.make_scene(P, W, H, C, seed, scale_mult=args.scale_mult).items()}
     cam = scenes.make_camera(W, H)
     gc, gd, gu = (g.to(dev) for g in scenes.make_upstream_grads(C, W, H, seed))
     st = ref.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=scene["bg"],
@@ -321,7 +335,8 @@ def run_reference(args, cfg, rank, world, local):
     return {"impl": "reference", "metric": "fwd+bwd views/sec", "value": value, "unit": "views/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded Gaussian cloud, SURVEY.md 8d)",
-            "config": {"workload": "%s: %d Gaussians, %dx%d, %d feature channels + depth + uncertainty, fwd+bwd" % (args.workload, P, W, H, C)},
+            "config": {"workload": "%s%s: %d Gaussians, %dx%d, %d feature channels + depth + uncertainty, fwd+bwd" % (
+                args.workload, "" if args.scale_mult == 1.0 else " heavy (splat scale x%g)" % args.scale_mult, P, W, H, C)},
             "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "clocks": clocks}
@@ -335,6 +350,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=["config2", "config3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scale-mult", type=float, default=1.0,
+                    help="multiply the synthetic splat scale (SURVEY 8d 'heavy' variant: 3.0); 1.0 is the BASELINE.json workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     from gscream_b200 import scenes
