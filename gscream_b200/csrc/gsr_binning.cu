@@ -153,47 +153,75 @@ BinningLayout binning_layout(int P, int64_t R, int W, int H)
 }
 
 // -------- kernels -----------------------------------------------------------------------------
-// Instance emission in depth order (the reference's duplicateWithKeys runs in index order and writes
-// 64-bit keys; here the depth is already encoded in the position, so the key is just the tile id).
+// Instance emission in depth order (the reference's duplicateWithKeys runs in index order, one thread per Gaussian,
+// and writes 64-bit keys; here the depth is already encoded in the position, so the key is just the tile id).
+// Warp-cooperative: the warp walks its 32 Gaussians one at a time and the lanes write that Gaussian's tile rectangle
+// as consecutive entries — coalesced stores instead of 32 interleaved single-entry streams (one thread per Gaussian
+// was L1-wavefront bound: 616 us at R = 40 M, profiles/r1_sort_ab.md).
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t *__restrict__ order,
                                                              const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ tiles_touched,
                                                              const float *__restrict__ rec, int gx, int gy,
                                                              uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
+	const int lane = threadIdx.x & 31;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= P) return;
-	const uint32_t g = order[i];
-	const uint32_t tt = tiles_touched[g];
-	if (tt == 0) return;
-	uint32_t off = offsets[i] - tt;
-	const float2 xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
-	const int radius = (int)rec[(size_t)g * GSR_REC_FLOATS + 13];
-	int x0, y0, x1, y1;
-	get_rect(xy.x, xy.y, radius, gx, gy, x0, y0, x1, y1); // same rect as the forward (CR/rasterizer_impl.cu:92)
-	for (int y = y0; y < y1; y++)
-		for (int x = x0; x < x1; x++) {
-			keys[off] = (uint32_t)(y * gx + x);
-			vals[off] = g;
-			off++;
+	uint32_t g = 0, tt = 0, off = 0;
+	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+	if (i < P) {
+		g = order[i];
+		tt = tiles_touched[g];
+		if (tt != 0) {
+			off = offsets[i] - tt;
+			const float2 xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
+			const int radius = (int)rec[(size_t)g * GSR_REC_FLOATS + 13];
+			get_rect(xy.x, xy.y, radius, gx, gy, x0, y0, x1, y1); // same rect as the forward (CR/rasterizer_impl.cu:92)
 		}
+	}
+	uint32_t todo = __ballot_sync(0xffffffffu, tt != 0);
+	while (todo) {
+		const int src = __ffs(todo) - 1;
+		todo &= todo - 1;
+		const uint32_t s_g = __shfl_sync(0xffffffffu, g, src), s_tt = __shfl_sync(0xffffffffu, tt, src);
+		const uint32_t s_off = __shfl_sync(0xffffffffu, off, src);
+		const int s_x0 = __shfl_sync(0xffffffffu, x0, src), s_y0 = __shfl_sync(0xffffffffu, y0, src);
+		const int w = __shfl_sync(0xffffffffu, x1, src) - s_x0;
+		// entry e of the rectangle in row-major order (y outer, x inner), as duplicateWithKeys emits it
+		for (uint32_t e = lane; e < s_tt; e += 32) {
+			const int ry = (int)e / w, rx = (int)e - ry * w;
+			keys[s_off + e] = (uint32_t)((s_y0 + ry) * gx + s_x0 + rx);
+			vals[s_off + e] = s_g;
+		}
+	}
 }
 
-// identifyTileRanges, CR/rasterizer_impl.cu:116-138, on 32-bit tile ids.
+// identifyTileRanges, CR/rasterizer_impl.cu:116-138, on 32-bit tile ids; 8 sorted keys per thread (two 16-B loads).
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint32_t *__restrict__ keys, uint2 *__restrict__ ranges)
 {
-	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= L) return;
-	const uint32_t cur = keys[idx];
-	if (idx == 0)
-		ranges[cur].x = 0;
-	else {
-		const uint32_t prev = keys[idx - 1];
-		if (cur != prev) {
+	const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+	if (base >= L) return;
+	uint32_t k[8];
+	if (base + 8 <= L) {
+		const uint4 a = __ldg(reinterpret_cast<const uint4 *>(keys + base)), b = __ldg(reinterpret_cast<const uint4 *>(keys + base + 4));
+		k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+	} else {
+#pragma unroll
+		for (int j = 0; j < 8; j++) k[j] = base + j < L ? __ldg(keys + base + j) : 0u;
+	}
+	uint32_t prev = base > 0 ? __ldg(keys + base - 1) : 0u;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const int64_t idx = base + j;
+		if (idx >= L) break;
+		const uint32_t cur = k[j];
+		if (idx == 0)
+			ranges[cur].x = 0;
+		else if (cur != prev) {
 			ranges[prev].y = (uint32_t)idx;
 			ranges[cur].x = (uint32_t)idx;
 		}
+		if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+		prev = cur;
 	}
-	if (idx == L - 1) ranges[cur].y = (uint32_t)L;
 }
 
 // -------- host orchestration --------------------------------------------------------------------
@@ -259,7 +287,7 @@ cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const Geom
 	                                   (uint32_t *)(binning + BL.val[1]), R, bits, binning + BL.temp, stream, &e);
 	if (e != cudaSuccess) return e;
 #endif
-	tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, (const uint32_t *)(binning + BL.key[which]), (uint2 *)(image + IL.ranges));
+	tile_ranges_kernel<<<(unsigned)((R + 2047) / 2048), 256, 0, stream>>>(R, (const uint32_t *)(binning + BL.key[which]), (uint2 *)(image + IL.ranges));
 	count_launch();
 	return cudaGetLastError();
 }

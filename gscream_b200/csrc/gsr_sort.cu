@@ -41,11 +41,15 @@ __global__ void __launch_bounds__(kRsThreads) rs_histogram_kernel(const uint32_t
 	s_hist[t] = 0;
 	__syncthreads();
 	const int64_t base = (int64_t)blockIdx.x * kRsTile;
-#pragma unroll 4
-	for (int i = 0; i < kRsItems; i++) {
+	uint32_t key[kRsItems];
+#pragma unroll
+	for (int i = 0; i < kRsItems; i++) { // all 16 loads in flight before the first shared-memory atomic
 		const int64_t idx = base + i * kRsThreads + t;
-		if (idx < n) atomicAdd(&s_hist[(__ldg(keys + idx) >> shift) & mask], 1u);
+		key[i] = idx < n ? __ldg(keys + idx) : 0u;
 	}
+#pragma unroll
+	for (int i = 0; i < kRsItems; i++)
+		if (base + i * kRsThreads + t < n) atomicAdd(&s_hist[(key[i] >> shift) & mask], 1u);
 	__syncthreads();
 	const uint32_t c = s_hist[t];
 	counts[(size_t)t * tiles + blockIdx.x] = c;
@@ -73,10 +77,11 @@ __global__ void __launch_bounds__(kRsThreads) rs_offsets_kernel(uint32_t *__rest
 }
 
 // stable scatter of one digit pass
-__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+__global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                                                                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
-                                                                int shift, uint32_t mask, const uint32_t *__restrict__ offsets, int tiles)
+                                                                int shift, int width, const uint32_t *__restrict__ offsets, int tiles)
 {
+	const uint32_t mask = (1u << width) - 1u;
 	__shared__ uint32_t s_hist[8][256]; // per-warp digit counts, then per-warp base inside the tile
 	__shared__ uint32_t s_tile_start[256];
 	__shared__ uint32_t s_goff[256];
@@ -93,7 +98,6 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint32_t *
 
 	// each warp owns the contiguous run [tile_base + warp*512, +512): element (i, lane) = run[i*32 + lane]
 	uint32_t key[kRsItems], val[kRsItems];
-	uint32_t rank[kRsItems];
 	const int64_t run_base = tile_base + warp * (kRsItems * 32);
 #pragma unroll
 	for (int i = 0; i < kRsItems; i++) {
@@ -102,17 +106,25 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint32_t *
 		key[i] = valid ? __ldg(keys_in + idx) : 0xFFFFFFFFu;
 		val[i] = valid ? __ldg(vals_in + idx) : 0u;
 	}
+	// lanes holding the same digit, by `width` ballots.  (The hardware MATCH.ANY iterates once per distinct value — up to
+	// 32 rounds per call on these keys — and made this kernel 10x slower, profiles/r1_sort_ab.md.)
+	auto peers_of = [&](uint32_t d, bool valid) -> uint32_t {
+		uint32_t m = __ballot_sync(0xffffffffu, valid);
+		for (int b = 0; b < width; b++) {
+			const bool bit = (d >> b) & 1u;
+			const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+			m &= bit ? bal : ~bal;
+		}
+		return m;
+	};
+	// pass A: this warp's digit counts (the lowest lane of every peer group adds the group size)
 #pragma unroll
 	for (int i = 0; i < kRsItems; i++) {
 		const bool valid = run_base + i * 32 + lane < n;
-		const uint32_t d = valid ? ((key[i] >> shift) & mask) : 0x100u; // invalid tail elements form their own group
-		const uint32_t m = __match_any_sync(0xffffffffu, d);
-		const uint32_t r = __popc(m & lt_mask);
-		const uint32_t prev = valid ? s_hist[warp][d] : 0u;
+		const uint32_t d = (key[i] >> shift) & mask;
+		const uint32_t m = peers_of(d, valid);
+		if (valid && (m & lt_mask) == 0) s_hist[warp][d] += __popc(m); // one writer per (warp, digit) per step
 		__syncwarp();
-		if (valid && r == 0) s_hist[warp][d] = prev + __popc(m); // lowest lane of the group advances the warp's counter
-		__syncwarp();
-		rank[i] = prev + r; // position among this warp's elements with digit d, in input order
 	}
 	__syncthreads();
 
@@ -127,17 +139,27 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint32_t *
 	const uint32_t tile_start = block_exclusive_scan_256(run, s_warp, nullptr);
 	s_tile_start[t] = tile_start;
 	s_goff[t] = run ? offsets[(size_t)t * tiles + blockIdx.x] : 0u;
+#pragma unroll
+	for (int w = 0; w < 8; w++) s_hist[w][t] += tile_start; // s_hist[w][d] = next free slot of (warp w, digit d) in the tile
 	__syncthreads();
 
-	// reorder through shared memory so that equal digits are contiguous (and still in input order)
+	// pass B: same peer groups again, now handing out slots in input order; reorder through shared memory so that equal
+	// digits are contiguous
 #pragma unroll
 	for (int i = 0; i < kRsItems; i++) {
-		if (run_base + i * 32 + lane < n) {
-			const uint32_t d = (key[i] >> shift) & mask;
-			const uint32_t pos = s_tile_start[d] + s_hist[warp][d] + rank[i];
-			s_keys[pos] = key[i];
-			s_vals[pos] = val[i];
+		const bool valid = run_base + i * 32 + lane < n;
+		const uint32_t d = (key[i] >> shift) & mask;
+		const uint32_t m = peers_of(d, valid);
+		uint32_t slot = 0;
+		if (valid) slot = s_hist[warp][d];
+		__syncwarp();
+		if (valid) {
+			const uint32_t r = __popc(m & lt_mask);
+			if (r == 0) s_hist[warp][d] = slot + __popc(m);
+			s_keys[slot + r] = key[i];
+			s_vals[slot + r] = val[i];
 		}
+		__syncwarp();
 	}
 	__syncthreads();
 	const int valid_count = (int)min((int64_t)kRsTile, n - tile_base);
@@ -182,7 +204,7 @@ int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint3
 		const uint32_t mask = (1u << width) - 1u;
 		rs_histogram_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, n, 8 * p, mask, pl.tiles, counts, totals + p * 256);
 		rs_offsets_kernel<<<256, kRsThreads, 0, stream>>>(counts, totals + p * 256, pl.tiles);
-		rs_scatter_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n, 8 * p, mask, counts, pl.tiles);
+		rs_scatter_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n, 8 * p, width, counts, pl.tiles);
 		count_launch(3);
 		std::swap(kin, kout);
 		std::swap(vin, vout);
