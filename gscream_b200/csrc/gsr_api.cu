@@ -4,7 +4,7 @@
 // position2D_filter,markVisible} orchestrate in the reference (CR/rasterizer_impl.cu:141-153,
 // 199-347, 350-406, 470-530, 536-643), on the caller's stream, with caller-owned scratch.
 #include "../../include/gsr_b200.h"
-#include "gsr_common.cuh"
+#include "gsr_internal.cuh"
 #include <atomic>
 
 namespace gsr {
@@ -32,52 +32,6 @@ struct StageTimer {
 	}
 	~StageTimer() { if (slot >= 0) cudaEventRecord(g_ev[st][slot][1], s); }
 };
-
-// implemented in the other translation units
-struct PreArgs {
-	int P, C, D, M;
-	const float *means3D, *scales, *rotations, *opacities, *uncertainties, *cov3D_precomp, *shs, *colors_precomp;
-	const float *view, *proj, *campos;
-	float scale_modifier;
-	int W, H;
-	float tan_fovx, tan_fovy, focal_x, focal_y;
-	int gx, gy;
-	int prefiltered;
-	int *radii;
-	float *rec;
-	uint32_t *tiles_touched, *depth_key, *depth_val;
-	float *pos_x, *pos_y;
-	uint8_t *clamped;
-	float *rgb;
-};
-struct PreBwdArgs {
-	int P, C, D, M;
-	const float *means3D, *scales, *rotations, *cov3D_precomp, *shs;
-	const float *view, *proj, *campos;
-	const uint8_t *clamped;
-	float scale_modifier;
-	int W, H;
-	float tan_fovx, tan_fovy, h_x, h_y;
-	const int *radii;
-	const float *gacc;
-	float *dL_dmeans2D, *dL_dopacity, *dL_duncertainty, *dL_dcolors;
-	float *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drotations;
-	int accumulate;
-};
-cudaError_t launch_preprocess(int mode, const PreArgs &a, cudaStream_t stream);
-cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t stream);
-cudaError_t launch_preprocess_backward(const PreBwdArgs &a, cudaStream_t stream);
-cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStream_t stream);
-cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const GeomLayout &GL, char *binning,
-                          const BinningLayout &BL, char *image, const ImageLayout &IL, cudaStream_t stream);
-int point_list_index(int W, int H);
-cudaError_t launch_blend_forward(int C, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
-                                 const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
-                                 float *out_depth, float *out_unc, cudaStream_t stream);
-cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
-                                  const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
-                                  const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
-                                  float *dL_dcolors, cudaStream_t stream);
 
 __global__ void export_records_kernel(int P, const float *__restrict__ rec, float *xy, float *depths, float *conic_opacity)
 {

@@ -20,7 +20,7 @@
 //
 // The stable radix sort and the prefix sum are hand-written (gsr_sort.cu).  Building with -DGSR_USE_CUB=1 swaps
 // in cub::DeviceRadixSort / cub::DeviceScan for A/B timing (profiles/r1_sort_ab.md); results are identical.
-#include "gsr_common.cuh"
+#include "gsr_internal.cuh"
 #include "gsr_sort.cuh"
 #include <algorithm>
 #ifndef GSR_USE_CUB

@@ -27,6 +27,7 @@
 // dopacity, ddepth, duncertainty}; colours into dL_dcolors[P][C].  Both must be zero (or hold the
 // running sum) on entry.
 #include "gsr_blend.cuh"
+#include "gsr_internal.cuh"
 
 #ifndef GSR_BWD_EARLYVOTE
 #define GSR_BWD_EARLYVOTE 0

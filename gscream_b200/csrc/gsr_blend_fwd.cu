@@ -21,6 +21,7 @@
 //     the reference `continue`s over, so results and n_contrib are unchanged;
 //   * Gaussian ids two batches ahead and slabs one batch ahead are in flight while the current one is blended.
 #include "gsr_blend.cuh"
+#include "gsr_internal.cuh"
 
 namespace gsr {
 

@@ -16,7 +16,7 @@
 // NOT compiled with fast-math.  Everything that is new here (bounding extents for the blend kernels'
 // culling) is computed from already-rounded values with explicit intrinsics, so it cannot perturb the
 // contraction of the reference expressions.
-#include "gsr_common.cuh"
+#include "gsr_internal.cuh"
 #include <cstdio>
 
 namespace gsr {
@@ -210,22 +210,6 @@ __device__ __forceinline__ void stage_rows(const float *__restrict__ g, int firs
 	}
 }
 
-struct PreArgs {
-	int P, C, D, M;
-	const float *means3D, *scales, *rotations, *opacities, *uncertainties, *cov3D_precomp, *shs, *colors_precomp;
-	const float *view, *proj, *campos;
-	float scale_modifier;
-	int W, H;
-	float tan_fovx, tan_fovy, focal_x, focal_y;
-	int gx, gy;
-	int prefiltered;
-	int *radii;
-	float *rec;
-	uint32_t *tiles_touched, *depth_key, *depth_val;
-	float *pos_x, *pos_y;
-	uint8_t *clamped;
-	float *rgb;
-};
 
 // MODE 0: full preprocess (K1); 1: visible_filter (radii only); 2: position2D_filter (radii + pixel x,y)
 template <int MODE>
@@ -388,20 +372,6 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float *_
 // gacc[P][8] holds what the blend backward accumulated: {dmean2D.x, dmean2D.y, dconic.x, dconic.y,
 // dconic.w, dopacity, ddepth, duncertainty}.
 // ------------------------------------------------------------------------------------------------
-struct PreBwdArgs {
-	int P, C, D, M;
-	const float *means3D, *scales, *rotations, *cov3D_precomp, *shs;
-	const float *view, *proj, *campos;
-	const uint8_t *clamped;
-	float scale_modifier;
-	int W, H;
-	float tan_fovx, tan_fovy, h_x, h_y;
-	const int *radii;
-	const float *gacc;
-	float *dL_dmeans2D, *dL_dopacity, *dL_duncertainty, *dL_dcolors;
-	float *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drotations;
-	int accumulate;
-};
 
 __device__ __forceinline__ void put(float *p, float v, int accumulate)
 {
