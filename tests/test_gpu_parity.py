@@ -284,15 +284,17 @@ def test_debug_mode_and_repeated_backward():
 
 
 # ---- (3) the reference's own CUDA build at BASELINE.json's full sizes ------------------------------------------
-@pytest.mark.parametrize("cfg", ["config2", "config3"])
-def test_full_size_against_reference_build(cfg):
+@pytest.mark.parametrize("cfg,smult", [("config2", 1.0), ("config3", 1.0), ("config3", 3.0)])
+def test_full_size_against_reference_build(cfg, smult):
+    """BASELINE.json configs[1] and configs[2] at full size, plus SURVEY 8d's 'heavy' variant (splat scale x3: ~40 tile
+    instances per Gaussian, ~4900-entry tile lists that terminate early)."""
     _require_native()
     c = scenes.CONFIGS[cfg]
     P, W, H, C, seed = c["P"], c["W"], c["H"], c["C"], c["seed"]
     if not ru.ref_available(C):
         pytest.skip("oracle/_ref/dgr%d not built (needs /root/reference at build time)" % C)
     ref_mod = ru.load_ref(C)
-    scene = scenes.make_scene(P, W, H, C, seed)
+    scene = scenes.make_scene(P, W, H, C, seed, scale_mult=smult)
     cam = scenes.make_camera(W, H)
     grads = scenes.make_upstream_grads(C, W, H, seed)
     r = ru.run_impl(ref_mod, scene, cam, grads)
