@@ -28,6 +28,13 @@ PROTOTYPES = {
     "gsr_position2d_filter": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "gsr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gsr_debug_export": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsr_decode_supported": (_i, [_i, _i]),
+    "gsr_decode_scratch_bytes": (_sz, [_i]),
+    "gsr_decode_stage1": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "gsr_decode_stage2": (_i, [_i, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsr_decode_backward": (_i, [_i, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_launch_count": (_i64, [_i]),
     "gsr_profile_enable": (_i, [_i]),
     "gsr_profile_read": (_i, [_i, _vp, _i]),

@@ -5,6 +5,7 @@
 // 199-347, 350-406, 470-530, 536-643), on the caller's stream, with caller-owned scratch.
 #include "../../include/gsr_b200.h"
 #include "gsr_internal.cuh"
+#include "gsr_decode.cuh"
 #include <atomic>
 
 namespace gsr {
@@ -16,7 +17,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // When enabled, every stage launch is bracketed by a cudaEvent pair on the caller's stream (a ring of
 // kProfCap pairs per stage).  Nothing is synchronised here; gsr_profile_read() is called after the
 // caller's own synchronise.  Disabled (the default) it costs one branch per stage.
-enum Stage { kPre = 0, kDepthScan, kBin, kBlendFwd, kBlendBwd, kPreBwd, kNumStages };
+enum Stage { kPre = 0, kDepthScan, kBin, kBlendFwd, kBlendBwd, kPreBwd, kDecodeFwd, kDecodeBwd, kNumStages };
 static constexpr int kProfCap = 256;
 static bool g_prof_on = false;
 static cudaEvent_t g_ev[kNumStages][kProfCap][2];
@@ -293,6 +294,96 @@ int gsr_mark_visible(int P, const float *means3D, const float *viewmatrix, const
 	if (P == 0) return 0;
 	if (!means3D || !viewmatrix || !present) return GSR_E_BADARG;
 	GSR_CUDA(launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream));
+	return 0;
+}
+
+// ---- anchor -> neural-Gaussian decode ---------------------------------------------------------------------------------
+int gsr_decode_supported(int feat_dim, int n_offsets) { return (feat_dim == 32 && n_offsets >= 1 && n_offsets <= kDecMaxK) ? 1 : 0; }
+size_t gsr_decode_scratch_bytes(int A) { return decode_layout(A).total; }
+
+static bool unpack_weights(const float *const *p, DecodeWeights &w)
+{
+	if (!p) return false;
+	for (int m = 0; m < 4; m++) {
+		w.w1[m] = p[4 * m + 0]; w.b1[m] = p[4 * m + 1]; w.w2[m] = p[4 * m + 2]; w.b2[m] = p[4 * m + 3];
+		if (!w.w1[m] || !w.b1[m] || !w.w2[m] || !w.b2[m]) return false;
+	}
+	return true;
+}
+
+int gsr_decode_stage1(int A, int feat_dim, int n_offsets, const float *anchor, const float *anchor_feat, const uint8_t *visible_mask,
+                      const float *campos, const float *const *mlp_params, void *scratch, size_t scratch_bytes, float *neural_opacity,
+                      uint8_t *mask, int64_t *counts_host, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (A < 0 || !counts_host || !gsr_decode_supported(feat_dim, n_offsets)) return GSR_E_BADARG;
+	counts_host[0] = visible_mask ? 0 : A;
+	counts_host[1] = 0;
+	if (A == 0) return 0;
+	DecodeWeights wt;
+	if (!anchor || !anchor_feat || !campos || !scratch || !neural_opacity || !mask || !unpack_weights(mlp_params, wt)) return GSR_E_BADARG;
+	const DecodeLayout L = decode_layout(A);
+	if (scratch_bytes < L.total || !aligned16(scratch)) return GSR_E_WORKSPACE;
+	StageTimer t(kDecodeFwd, stream);
+	GSR_CUDA(decode_stage1(A, n_offsets, anchor, anchor_feat, visible_mask, campos, wt, (char *)scratch, L, neural_opacity, mask, counts_host, stream));
+	return 0;
+}
+
+static int fill_decode_args(DecodeArgs &a, int A, int feat_dim, int n_offsets, int64_t n_vis, int64_t P, const float *anchor,
+                            const float *anchor_feat, const float *offset, const float *scaling, const float *campos,
+                            const float *const *mlp_params, void *scratch, size_t scratch_bytes)
+{
+	if (A <= 0 || n_vis < 0 || n_vis > A || P < 0 || P > n_vis * n_offsets || !gsr_decode_supported(feat_dim, n_offsets)) return GSR_E_BADARG;
+	if (!anchor || !anchor_feat || !offset || !scaling || !campos || !scratch || !unpack_weights(mlp_params, a.wt)) return GSR_E_BADARG;
+	const DecodeLayout L = decode_layout(A);
+	if (scratch_bytes < L.total || !aligned16(scratch)) return GSR_E_WORKSPACE;
+	char *s = (char *)scratch;
+	a.k = n_offsets; a.n_vis = (int)n_vis; a.n_vis_dev = nullptr;
+	a.vis_ids = n_vis == A ? nullptr : (const uint32_t *)(s + L.vis_ids); // all visible: the list is the identity
+	a.anchor = anchor; a.feat = anchor_feat; a.offset = offset; a.scaling = scaling; a.campos = campos;
+	a.count = (uint32_t *)(s + L.count); a.maskbits = (uint32_t *)(s + L.maskbits); a.gauss_incl = (const uint32_t *)(s + L.gauss_incl);
+	return 0;
+}
+
+int gsr_decode_stage2(int A, int feat_dim, int n_offsets, int64_t n_vis, int64_t P, const float *anchor, const float *anchor_feat,
+                      const float *offset, const float *scaling, const float *campos, const float *const *mlp_params, void *scratch,
+                      size_t scratch_bytes, const float *neural_opacity, float *xyz, float *color, float *opacity, float *uncertainty,
+                      float *out_scaling, float *rot, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (A == 0 || n_vis == 0 || P == 0) return (A < 0 || n_vis < 0 || P < 0) ? GSR_E_BADARG : 0;
+	DecodeArgs a{};
+	const int rc = fill_decode_args(a, A, feat_dim, n_offsets, n_vis, P, anchor, anchor_feat, offset, scaling, campos, mlp_params, scratch, scratch_bytes);
+	if (rc) return rc;
+	if (!neural_opacity || !xyz || !color || !opacity || !uncertainty || !out_scaling || !rot) return GSR_E_BADARG;
+	a.neural_opacity = const_cast<float *>(neural_opacity);
+	a.out_xyz = xyz; a.out_color = color; a.out_opacity = opacity; a.out_uncertainty = uncertainty; a.out_scaling = out_scaling; a.out_rot = rot;
+	StageTimer t(kDecodeFwd, stream);
+	GSR_CUDA(decode_stage2(a, stream));
+	return 0;
+}
+
+int gsr_decode_backward(int A, int feat_dim, int n_offsets, int64_t n_vis, int64_t P, const float *anchor, const float *anchor_feat,
+                        const float *offset, const float *scaling, const float *campos, const float *const *mlp_params, void *scratch,
+                        size_t scratch_bytes, const float *d_xyz, const float *d_color, const float *d_opacity, const float *d_uncertainty,
+                        const float *d_scaling, const float *d_rot, const float *d_neural_opacity, float *g_anchor, float *g_feat,
+                        float *g_offset, float *g_scaling, float *const *g_mlp_params, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (A == 0 || n_vis == 0) return (A < 0 || n_vis < 0) ? GSR_E_BADARG : 0;
+	DecodeBwdArgs b{};
+	const int rc = fill_decode_args(b.f, A, feat_dim, n_offsets, n_vis, P, anchor, anchor_feat, offset, scaling, campos, mlp_params, scratch, scratch_bytes);
+	if (rc) return rc;
+	if (!g_anchor || !g_feat || !g_offset || !g_scaling || !g_mlp_params) return GSR_E_BADARG;
+	for (int m = 0; m < 4; m++) {
+		b.g_w1[m] = g_mlp_params[4 * m + 0]; b.g_b1[m] = g_mlp_params[4 * m + 1]; b.g_w2[m] = g_mlp_params[4 * m + 2]; b.g_b2[m] = g_mlp_params[4 * m + 3];
+		if (!b.g_w1[m] || !b.g_b1[m] || !b.g_w2[m] || !b.g_b2[m]) return GSR_E_BADARG;
+	}
+	b.d_xyz = d_xyz; b.d_color = d_color; b.d_opacity = d_opacity; b.d_uncertainty = d_uncertainty; b.d_scaling = d_scaling; b.d_rot = d_rot;
+	b.d_neural_opacity = d_neural_opacity;
+	b.g_anchor = g_anchor; b.g_feat = g_feat; b.g_offset = g_offset; b.g_scaling = g_scaling;
+	StageTimer t(kDecodeBwd, stream);
+	GSR_CUDA(decode_backward(b, stream));
 	return 0;
 }
 

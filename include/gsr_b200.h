@@ -147,6 +147,48 @@ GSR_API int gsr_mark_visible(
     uint8_t *present, gsr_stream_t stream);
 
 /*
+ * Anchor -> neural-Gaussian decode — replaces generate_neural_gaussians
+ * (gaussian_renderer/__init__.py:18-102 of W-Ted/GScream, use_feat_bank = False): visible-anchor gather, the view
+ * features ob_view / ob_dist, the four 36->32->{k, k, 7k, 3k} MLPs (scene/gaussian_model.py:118-144), the
+ * neural_opacity > 0 selection and the post-processing into the rasterizer's inputs.  Like the rasterizer it is split
+ * at the one host sync the reference's interface forces (the output sizes are data dependent).
+ *   anchor[A,3] anchor_feat[A,32] offset[A,k,3] scaling[A,6] (= exp(_scaling), scene/gaussian_model.py:241-242)
+ *   visible_mask[A] bytes (0 / non-0) or NULL for "all anchors"; campos[3]
+ *   mlp_params: HOST array of 16 device pointers, torch.nn.Linear layout, in the order
+ *               {opacity, uncertainty, cov, colour} x {w1[32,36], b1[32], w2[n_out,32], b2[n_out]}, n_out = k, k, 7k, 3k
+ *   scratch: gsr_decode_scratch_bytes(A) bytes; written by stage 1, read by stage 2 and by the backward.
+ * feat_dim must be 32 and 1 <= n_offsets <= 16 (gsr_decode_supported), else GSR_E_BADARG.
+ *
+ * Stage 1: neural_opacity[A*k] (tanh of the opacity MLP, rows of visible anchors in order, first n_vis*k entries valid),
+ *          mask[A*k] (neural_opacity > 0), counts_host (PINNED int64[2], pre-zeroed by the callee): [0] n_vis, [1] P.
+ */
+GSR_API int gsr_decode_supported(int feat_dim, int n_offsets);
+GSR_API size_t gsr_decode_scratch_bytes(int A);
+GSR_API int gsr_decode_stage1(
+    int A, int feat_dim, int n_offsets,
+    const float *anchor, const float *anchor_feat, const uint8_t *visible_mask, const float *campos,
+    const float *const *mlp_params, void *scratch, size_t scratch_bytes,
+    float *neural_opacity, uint8_t *mask, int64_t *counts_host, gsr_stream_t stream);
+/* Stage 2: xyz[P,3] color[P,3] opacity[P] uncertainty[P] out_scaling[P,3] rot[P,4] of the kept offsets, in
+ * (visible anchor, offset) order — gaussian_renderer/__init__.py:66-101. */
+GSR_API int gsr_decode_stage2(
+    int A, int feat_dim, int n_offsets, int64_t n_vis, int64_t P,
+    const float *anchor, const float *anchor_feat, const float *offset, const float *scaling, const float *campos,
+    const float *const *mlp_params, void *scratch, size_t scratch_bytes, const float *neural_opacity,
+    float *xyz, float *color, float *opacity, float *uncertainty, float *out_scaling, float *rot, gsr_stream_t stream);
+/* Backward of both stages.  Upstream gradients (any may be NULL = zero): d_xyz[P,3] d_color[P,3] d_opacity[P]
+ * d_uncertainty[P] d_scaling[P,3] d_rot[P,4] and d_neural_opacity[n_vis*k].  Outputs g_anchor[A,3] g_feat[A,32]
+ * g_offset[A,k,3] g_scaling[A,6] must arrive zero-filled (rows of invisible anchors are not touched);
+ * g_mlp_params (HOST array of 16 device pointers, same order as mlp_params) is accumulated into. */
+GSR_API int gsr_decode_backward(
+    int A, int feat_dim, int n_offsets, int64_t n_vis, int64_t P,
+    const float *anchor, const float *anchor_feat, const float *offset, const float *scaling, const float *campos,
+    const float *const *mlp_params, void *scratch, size_t scratch_bytes,
+    const float *d_xyz, const float *d_color, const float *d_opacity, const float *d_uncertainty,
+    const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
+    float *g_anchor, float *g_feat, float *g_offset, float *g_scaling, float *const *g_mlp_params, gsr_stream_t stream);
+
+/*
  * Introspection for parity tests (device -> device copies out of the private scratch layout).
  * Any output pointer may be NULL.  Shapes: xy[P,2] depths[P] conic_opacity[P,4]
  * tiles_touched[P] point_list[R] ranges[tiles,2] final_T[H*W] n_contrib[H*W].
@@ -165,7 +207,7 @@ GSR_API int gsr_debug_export(
  * synchronised); gsr_profile_enable(0) stops.  After the caller has synchronised, gsr_profile_read() copies the
  * elapsed milliseconds of the recorded launches of one stage to HOST memory and returns how many there were.
  * Stages: 0 preprocess, 1 depth order + scan, 2 instance binning, 3 blend forward, 4 blend backward,
- * 5 per-Gaussian backward.
+ * 5 per-Gaussian backward, 6 decode forward (stages 1 + 2), 7 decode backward.
  */
 GSR_API int gsr_profile_enable(int on);
 GSR_API int gsr_profile_read(int stage, float *ms_host, int capacity);

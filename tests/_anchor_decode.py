@@ -30,6 +30,30 @@ class SyntheticAnchors(nn.Module):
         self.mlp_cov = nn.Sequential(nn.Linear(d, feat_dim), nn.ReLU(True), nn.Linear(feat_dim, 7 * n_offsets))
         self.mlp_color = nn.Sequential(nn.Linear(d, feat_dim), nn.ReLU(True), nn.Linear(feat_dim, 3 * n_offsets), nn.Sigmoid())
 
+    # attribute names of scene/gaussian_model.py:229-272, so the reference's own function accepts this object
+    use_feat_bank = False
+    rotation_activation = staticmethod(torch.nn.functional.normalize)
+
+    @property
+    def get_anchor(self):
+        return self._anchor
+
+    @property
+    def get_opacity_mlp(self):
+        return self.mlp_opacity
+
+    @property
+    def get_uncertainty_mlp(self):
+        return self.mlp_uncertainty
+
+    @property
+    def get_cov_mlp(self):
+        return self.mlp_cov
+
+    @property
+    def get_color_mlp(self):
+        return self.mlp_color
+
     @property
     def get_scaling(self):
         return 1.0 * torch.exp(self._scaling)          # scene/gaussian_model.py:241-242
