@@ -63,7 +63,10 @@ def load():
             "libgsr_b200.so is missing (%s). Build it with `python -m gscream_b200._build` "
             "(or __graft_entry__.build()); there is no CPU fallback." % path)
     lib = ctypes.CDLL(path)
+    ab_variant = bool(os.environ.get("GSR_LIB_PATH"))
     for name, (res, args) in PROTOTYPES.items():
+        if ab_variant and not hasattr(lib, name):
+            continue  # an older A/B build of the library (development aid only): symbols added later are absent
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args

@@ -49,6 +49,14 @@ __global__ void export_records_kernel(int P, const float *__restrict__ rec, floa
 	}
 }
 
+// point_list entries carry the per-warp overlap mask in their top byte (gsr_common.cuh: point_list_packed); the export
+// returns plain Gaussian ids like the reference's point_list (CR/rasterizer_impl.h:55-62)
+__global__ void export_point_list_kernel(int64_t R, const uint32_t *__restrict__ src, uint32_t mask, uint32_t *__restrict__ dst)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < R) dst[i] = src[i] & mask;
+}
+
 static bool channels_ok(int C) { return C == 3 || C == 32; }
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -156,7 +164,7 @@ int gsr_forward_stage2(int P, int C, int64_t num_rendered, const float *colors_p
 	{ StageTimer t(kBin, stream); GSR_CUDA(bin_instances(P, num_rendered, width, height, geom, GL, binning, BL, image, IL, stream)); }
 	{
 		StageTimer t(kBlendFwd, stream);
-		GSR_CUDA(launch_blend_forward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
+		GSR_CUDA(launch_blend_forward(C, P, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
 		                              (const float *)(geom + GL.rec), colors_precomp, background, (float *)(image + IL.final_T),
 		                              (uint32_t *)(image + IL.n_contrib), out_color, out_depth, out_uncertainty, stream));
 	}
@@ -197,7 +205,7 @@ int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const
 	count_launch(2);
 	if (num_rendered > 0) {
 		StageTimer t(kBlendBwd, stream);
-		GSR_CUDA(launch_blend_backward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
+		GSR_CUDA(launch_blend_backward(C, P, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
 		                               (const float *)(geom + GL.rec), colors_precomp, background, (const float *)(image + IL.final_T),
 		                               (const uint32_t *)(image + IL.n_contrib), dL_dout_color, dL_dout_depth, dL_dout_uncertainty, gacc,
 		                               dL_dcolors, stream));
@@ -404,8 +412,11 @@ int gsr_debug_export(int P, int64_t num_rendered, int width, int height, const v
 		GSR_CUDA(cudaGetLastError());
 	}
 	if (geom && tiles_touched) GSR_CUDA(cudaMemcpyAsync(tiles_touched, geom + GL.tiles_touched, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream));
-	if (binning && point_list && num_rendered > 0)
-		GSR_CUDA(cudaMemcpyAsync(point_list, binning + BL.val[point_list_index(width, height)], (size_t)num_rendered * 4, cudaMemcpyDeviceToDevice, stream));
+	if (binning && point_list && num_rendered > 0) {
+		export_point_list_kernel<<<(unsigned)((num_rendered + 255) / 256), 256, 0, stream>>>(
+		    num_rendered, (const uint32_t *)(binning + BL.val[point_list_index(width, height)]), point_list_packed(P) ? 0x00FFFFFFu : 0xFFFFFFFFu, point_list);
+		GSR_CUDA(cudaGetLastError());
+	}
 	if (image && ranges) GSR_CUDA(cudaMemcpyAsync(ranges, image + IL.ranges, tiles * 8, cudaMemcpyDeviceToDevice, stream));
 	if (image && final_T) GSR_CUDA(cudaMemcpyAsync(final_T, image + IL.final_T, N * 4, cudaMemcpyDeviceToDevice, stream));
 	if (image && n_contrib) GSR_CUDA(cudaMemcpyAsync(n_contrib, image + IL.n_contrib, N * 4, cudaMemcpyDeviceToDevice, stream));

@@ -160,19 +160,21 @@ BinningLayout binning_layout(int P, int64_t R, int W, int H)
 // was L1-wavefront bound: 616 us at R = 40 M, profiles/r1_sort_ab.md).
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t *__restrict__ order,
                                                              const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ tiles_touched,
-                                                             const float *__restrict__ rec, int gx, int gy,
+                                                             const float *__restrict__ rec, int gx, int gy, bool packed,
                                                              uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
 	const int lane = threadIdx.x & 31;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t g = 0, tt = 0, off = 0;
 	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+	float2 xy = {0.f, 0.f}, ext = {-1.f, -1.f};
 	if (i < P) {
 		g = order[i];
 		tt = tiles_touched[g];
 		if (tt != 0) {
 			off = offsets[i] - tt;
-			const float2 xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
+			xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
+			ext = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS + 8);
 			const int radius = (int)rec[(size_t)g * GSR_REC_FLOATS + 13];
 			get_rect(xy.x, xy.y, radius, gx, gy, x0, y0, x1, y1); // same rect as the forward (CR/rasterizer_impl.cu:92)
 		}
@@ -185,11 +187,17 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 		const uint32_t s_off = __shfl_sync(0xffffffffu, off, src);
 		const int s_x0 = __shfl_sync(0xffffffffu, x0, src), s_y0 = __shfl_sync(0xffffffffu, y0, src);
 		const int w = __shfl_sync(0xffffffffu, x1, src) - s_x0;
-		// entry e of the rectangle in row-major order (y outer, x inner), as duplicateWithKeys emits it
+		const float s_cx = __shfl_sync(0xffffffffu, xy.x, src), s_cy = __shfl_sync(0xffffffffu, xy.y, src);
+		const float s_hx = __shfl_sync(0xffffffffu, ext.x, src), s_hy = __shfl_sync(0xffffffffu, ext.y, src);
+		// entry e of the rectangle in row-major order (y outer, x inner), as duplicateWithKeys emits it; the value carries
+		// the 8-bit mask of the tile's warps whose pixel block the alpha >= 1/255 bounding box touches (gsr_blend.cuh)
 		for (uint32_t e = lane; e < s_tt; e += 32) {
 			const int ry = (int)e / w, rx = (int)e - ry * w;
-			keys[s_off + e] = (uint32_t)((s_y0 + ry) * gx + s_x0 + rx);
-			vals[s_off + e] = s_g;
+			const int tx = s_x0 + rx, ty = s_y0 + ry;
+			keys[s_off + e] = (uint32_t)(ty * gx + tx);
+			uint32_t v = s_g;
+			if (packed) v |= warp_overlap_mask(s_cx, s_cy, s_hx, s_hy, (float)(tx * GSR_BLOCK_X), (float)(ty * GSR_BLOCK_Y)) << 24;
+			vals[s_off + e] = v;
 		}
 	}
 }
@@ -269,7 +277,7 @@ cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const Geom
 	const uint32_t *order = (const uint32_t *)(geom + GL.depth_val[depth_order_index()]);
 	emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order, (const uint32_t *)(geom + GL.offsets),
 	                                                         (const uint32_t *)(geom + GL.tiles_touched), (const float *)(geom + GL.rec),
-	                                                         gx, gy, (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
+	                                                         gx, gy, point_list_packed(P), (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
 	count_launch();
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return e;

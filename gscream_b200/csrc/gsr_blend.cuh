@@ -1,114 +1,146 @@
 // gsr_blend.cuh — pieces shared by the forward and backward tile-blend kernels.
+//
+// Staging scheme (v2, "warp-private feeds").  A 16x16 tile is blended by 8 warps, warp w owning an 8x4 pixel block.
+// Each instance of the tile's depth-sorted list carries, in the top byte of its point_list entry, an 8-bit mask of the
+// warps whose pixel block its alpha >= 1/255 bounding box touches (written by the instance emission, gsr_binning.cu).
+// Every warp runs its own pipeline over the list, with no block-level barrier anywhere:
+//   scan    : 64 list entries per step (two coalesced 4-B loads per lane, prefetched two steps ahead), ballot-compacted
+//             into the warp's ring of (Gaussian id, list position) — only entries whose mask names this warp;
+//   gather  : the next 16 ring entries' projected records (and feature rows) are copied into one of the warp's two
+//             private stage buffers with 16-B cp.async (LDGSTS), one chunk ahead of the arithmetic;
+//   blend   : the per-pixel recurrence runs over the landed chunk, entries in order, operands broadcast from shared memory.
+// v1 staged every instance of the tile once per CTA behind a per-round __syncthreads(); ncu showed 18-19 % of the warp
+// samples waiting at that barrier for the slowest warp of the round (profiles/r1_blend_v3_summary.md).  v2 trades ~1.4x more
+// L2->SM gather traffic (an instance is fetched by each warp that needs it) for fully decoupled warps, a per-warp early
+// exit in the forward and a per-warp start position in the backward.  A/B: profiles/r1_feed_ab.md.
 #pragma once
 #include "gsr_common.cuh"
 
 namespace gsr {
 
-#ifndef GSR_BATCH
-#define GSR_BATCH 128
+constexpr int kWarpsPerTile = 8;     // warp w of a tile owns an 8x4 pixel block of the 16x16 tile
+// Warps never synchronise with each other, so the CTA is only a residency unit: a tile is blended by 8 / WPC CTAs of WPC
+// warps.  Small CTAs return their SM slots as soon as their own warps are done instead of waiting for the slowest warp
+// of the tile.  Measured (profiles/r1_feed_ab.md): the forward kernel is fastest with one warp per CTA (32 resident CTAs
+// per SM), the backward kernel with two.
+#ifndef GSR_FWD_WARPS_PER_CTA
+#define GSR_FWD_WARPS_PER_CTA 1
 #endif
-constexpr int kBatch = GSR_BATCH;    // Gaussians staged per round
-constexpr int kStages = 2;           // double-buffered slabs (cp.async groups)
-constexpr int kIdStages = 3;         // ids / masks are triple-buffered so one barrier per round suffices
-constexpr int kWarpsPerTile = 8;     // 256 threads; warp w owns an 8x4 pixel block of the 16x16 tile
+#ifndef GSR_BWD_WARPS_PER_CTA
+#define GSR_BWD_WARPS_PER_CTA 2
+#endif
+static_assert(kWarpsPerTile % GSR_FWD_WARPS_PER_CTA == 0 && kWarpsPerTile % GSR_BWD_WARPS_PER_CTA == 0, "warps per CTA must divide 8");
+constexpr int kChunk = 16;           // ring entries gathered / blended per pipeline step
+constexpr int kScan = 64;            // list entries scanned per refill (two per lane)
+constexpr int kRing = 128;           // ring capacity (>= kScan + 2 * kChunk + kChunk)
+constexpr uint32_t kIdMask = 0x00FFFFFFu;  // low 24 bits of a packed point_list entry: the Gaussian id
 constexpr float kAlphaMin = 1.0f / 255.0f;
 
 template <int C>
 struct BlendTraits {
-	// C <= 3: colours ride in the 64-B record (slots 10..12); otherwise one row of colors_precomp
-	// (C*4 bytes, a multiple of 16) is gathered next to the record.
+	// C <= 3: colours ride in the 64-B record (slots 10..12), the whole record is staged.  Otherwise the blend loops need
+	// only the first 32 B of the record (x y a b | c opacity depth uncertainty) plus the C*4-B row of colors_precomp.
 	static constexpr bool kFeatInRec = (C <= 3);
-	static constexpr int kFeatFloats = kFeatInRec ? 0 : C;
-	static constexpr uint32_t kBytesPerGaussian = GSR_REC_BYTES + kFeatFloats * 4;
-	static constexpr size_t kStageBytes = (size_t)kBatch * kBytesPerGaussian;
-	// dynamic shared memory: kStages x [rec kBatch x 64 B][feat kBatch x C*4 B], then
-	// [ids 3 x kBatch u32][masks 3 x kBatch u8][warp lists 8 x kBatch u8]
-	static constexpr size_t kIdsOff = kStages * kStageBytes;
-	static constexpr size_t kMaskOff = kIdsOff + (size_t)kIdStages * kBatch * 4;
-	static constexpr size_t kListOff = kMaskOff + (size_t)kIdStages * kBatch;
-	static constexpr size_t kSmemBytes = kListOff + (size_t)kWarpsPerTile * kBatch;
+	static constexpr int kRecParts = kFeatInRec ? 4 : 2;      // 16-B parts
+	static constexpr int kFeatParts = kFeatInRec ? 0 : C / 4;
+	static constexpr int kParts = kRecParts + kFeatParts;
+	static constexpr int kEntryFloats = kParts * 4;
+	static constexpr int kStageFloats = kChunk * kEntryFloats;
+	// per warp: two stage buffers, then the ring (ids, positions)
+	static constexpr int kWarpBytes = 2 * kStageFloats * 4 + kRing * 8;
 };
 
-// 16-byte asynchronous global->shared copy (Ampere-style cp.async, SASS LDGSTS; L2 only, no L1 allocation).
-// Measured against per-Gaussian bulk copies (cp.async.bulk / UBLKCP): a bulk copy takes its operands from
-// uniform registers, so 32 lanes gathering 32 different rows serialise into 32 elect/R2UR/UBLKCP rounds
-// (16 issue slots per Gaussian, 13 % of the forward kernel's instructions in profiles/r1_blend_v1), whereas
-// one LDGSTS moves 512 B for the whole warp.  See DESIGN.md section "staging".
+// 16-byte asynchronous global->shared copy (cp.async, SASS LDGSTS; L2 only, no L1 allocation).
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
 {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-// Slab staging of one batch (`count` Gaussians) into shared-memory stage buffers.  Two interchangeable engines:
-//   BULK = true : one cp.async.bulk (TMA, SASS UBLKCP) per record and per feature row, issued by the thread that
-//                 owns the Gaussian, completing on the stage's mbarrier (expect_tx by thread 0).  Uses the async
-//                 proxy: no LSU / L1 involvement, but each copy takes its operands from uniform registers, so a
-//                 warp's 32 gathers serialise into 32 elect/R2UR/UBLKCP rounds (~16 issue slots per Gaussian).
-//   BULK = false: 16-B cp.async (SASS LDGSTS) chunks assigned to threads in order: 12 instructions per thread per
-//                 128-Gaussian batch at C = 32, but they travel through the LSU pipe that the inner loops' LDS also use.
-// Both were measured (profiles/r1_*): forward is indifferent, backward prefers BULK by ~5 %.
-// Defaults chosen from the A/B in profiles/r1_staging_ab.md: forward -> LDGSTS, backward -> bulk (TMA).
-#ifndef GSR_FWD_BULK
-#define GSR_FWD_BULK 0
-#endif
-#ifndef GSR_BWD_BULK
-#define GSR_BWD_BULK 1
-#endif
-
-template <int C, bool kStageBulk>
-__device__ __forceinline__ void stage_init(uint64_t *bars, int tid)
-{
-	if (kStageBulk) {
-		if (tid == 0) {
-			for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
-			mbar_fence_init();
-		}
-	}
-}
-// `my_id` is the Gaussian owned by thread tid (< count); `s_ids` holds the same ids for the chunked engine.
-template <int C, bool kStageBulk>
-__device__ __forceinline__ void stage_issue(uint64_t *bar, float *s_rec, float *s_feat, const uint32_t *s_ids, uint32_t my_id, int count,
-                                            const float *__restrict__ rec, const float *__restrict__ features, int tid)
-{
+// One warp's feed over its tile's list.  kReverse: scan back to front starting at list position n-1 (backward pass).
+// All members are warp-uniform except `lane`-dependent temporaries.
+template <int C, bool kReverse>
+struct WarpFeed {
 	using TR = BlendTraits<C>;
-	if (kStageBulk) {
-		if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)count * TR::kBytesPerGaussian);
-		if (tid < count) {
-			bulk_g2s(s_rec + tid * GSR_REC_FLOATS, rec + (size_t)my_id * GSR_REC_FLOATS, GSR_REC_BYTES, bar);
-			if constexpr (!TR::kFeatInRec) bulk_g2s(s_feat + tid * C, features + (size_t)my_id * C, C * 4, bar);
-		}
-	} else {
+	const uint32_t *list;      // point_list + range.x
+	const float *rec, *feat;
+	float *stage;              // [2][kChunk][kEntryFloats]
+	uint32_t *q_id, *q_pos;    // [kRing]
+	int n, next_scan;          // list positions to scan; next scan step (in units of kScan)
+	uint32_t tail, issued, done;
+	uint32_t pre0a, pre0b, pre1a, pre1b;  // entries of the next two scan steps (two per lane each)
+	int warp, lane;
+	int lane_e, lane_part;     // gather role of this lane: entry offset within a group of kGroup entries, 16-B part (or -1: idle)
+	bool packed;
+	static constexpr int kGroup = 32 / TR::kParts;  // entries gathered per warp-wide cp.async round
+
+	__device__ __forceinline__ int pos_of(int ordinal) const { return kReverse ? n - 1 - ordinal : ordinal; }
+	__device__ __forceinline__ uint32_t load_entry(int ordinal) const { return ordinal < n ? __ldg(list + pos_of(ordinal)) : 0u; }
+
+	__device__ __forceinline__ void init(unsigned char *warp_smem, const uint32_t *list_, int n_, const float *rec_, const float *feat_,
+	                                     int warp_, int lane_, bool packed_)
+	{
+		stage = reinterpret_cast<float *>(warp_smem);
+		q_id = reinterpret_cast<uint32_t *>(warp_smem + 2 * TR::kStageFloats * 4);
+		q_pos = q_id + kRing;
+		list = list_; n = n_; rec = rec_; feat = feat_; warp = warp_; lane = lane_; packed = packed_;
+		lane_e = lane / TR::kParts;
+		lane_part = lane_e < kGroup ? lane - lane_e * TR::kParts : -1;
+		next_scan = 0;
+		tail = issued = done = 0;
+		pre0a = load_entry(lane); pre0b = load_entry(32 + lane);
+		pre1a = load_entry(kScan + lane); pre1b = load_entry(kScan + 32 + lane);
+	}
+	__device__ __forceinline__ bool exhausted() const { return next_scan * kScan >= n; }
+
+	// consume one prefetched scan step into the ring, start the load of the step after the next
+	__device__ __forceinline__ void refill()
+	{
+		const int base = next_scan * kScan;
 #pragma unroll
-		for (int k = 0; k < (kBatch * 4) / 256; k++) {
-			const int q = tid + 256 * k, row = q >> 2, part = q & 3;
-			if (row < count) cp_async16(s_rec + row * GSR_REC_FLOATS + part * 4, rec + (size_t)s_ids[row] * GSR_REC_FLOATS + part * 4);
-		}
-		if constexpr (!TR::kFeatInRec) {
-			constexpr int kChunksPerRow = C / 4;
-#pragma unroll
-			for (int k = 0; k < (kBatch * kChunksPerRow + 255) / 256; k++) {
-				const int q = tid + 256 * k, row = q / kChunksPerRow, part = q % kChunksPerRow;
-				if (row < count) cp_async16(s_feat + row * C + part * 4, features + (size_t)s_ids[row] * C + part * 4);
+		for (int c = 0; c < 2; c++) {
+			const uint32_t v = c == 0 ? pre0a : pre0b;
+			const int ordinal = base + 32 * c + lane;
+			const bool hit = ordinal < n && (!packed || ((v >> (24 + warp)) & 1u));
+			const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+			if (hit) {
+				const uint32_t idx = (tail + __popc(ball & ((1u << lane) - 1u))) & (kRing - 1);
+				q_id[idx] = packed ? (v & kIdMask) : v;
+				q_pos[idx] = (uint32_t)pos_of(ordinal);
 			}
+			tail += __popc(ball);
+		}
+		pre0a = pre1a; pre0b = pre1b;
+		next_scan++;
+		pre1a = load_entry((next_scan + 1) * kScan + lane);
+		pre1b = load_entry((next_scan + 1) * kScan + 32 + lane);
+	}
+	// keep two chunks queued ahead of the gather whenever the list allows
+	__device__ __forceinline__ void fill()
+	{
+		while ((int)(tail - issued) < 2 * kChunk && !exhausted()) refill();
+		__syncwarp();
+	}
+	// gather the next (up to) kChunk ring entries into stage buffer `s`; always commits one cp.async group
+	__device__ __forceinline__ int issue(int s)
+	{
+		const int m = min(kChunk, (int)(tail - issued));
+		float *dst = stage + s * TR::kStageFloats;
+		// lane -> (entry e0 + lane_e, part lane_part): kGroup entries per round, no index arithmetic in the loop
+		const bool is_rec = lane_part < TR::kRecParts;
+		const float *base = is_rec ? rec + lane_part * 4 : feat + (lane_part - TR::kRecParts) * 4;
+		const uint32_t stride = is_rec ? GSR_REC_FLOATS : C;
+		float *d = dst + lane_e * TR::kEntryFloats + lane_part * 4;
+		for (int e = lane_e; e < m; e += kGroup, d += kGroup * TR::kEntryFloats) {
+			if (lane_part >= 0) cp_async16(d, base + (size_t)q_id[(issued + e) & (kRing - 1)] * stride);
 		}
 		cp_async_commit();
+		issued += m;
+		return m;
 	}
-}
-// Wait until the batch staged as the `use`-th use of this stage buffer has landed (for this thread's view;
-// the caller's block barrier publishes it to everyone in the chunked engine).
-template <bool kStageBulk>
-__device__ __forceinline__ void stage_wait(uint64_t *bar, int use)
-{
-	if (kStageBulk) mbar_wait(bar, (uint32_t)(use & 1));
-	else cp_async_wait_all();
-}
-template <bool kStageBulk>
-__device__ __forceinline__ void stage_drain()
-{
-	if (!kStageBulk) cp_async_wait_all();
-}
+};
 
 // power = -0.5 (a dx^2 + c dy^2) - b dx dy, CR/forward.cu:524 / CR/backward.cu:524, with the rounding
 // sequence of the reference build's SASS (same in renderCUDA forward and backward, C = 3 and 32):
@@ -126,48 +158,6 @@ __device__ __forceinline__ void warp_block_origin(int warp, int &bx, int &by)
 {
 	bx = (warp & 1) * 8;
 	by = (warp >> 1) * 4;
-}
-
-// One bit per warp: does the bounding box {|x - cx| <= hx, |y - cy| <= hy} of the Gaussian's
-// alpha >= 1/255 region touch that warp's 8x4 pixel block?  (Pixel centres are integer coordinates,
-// CR/forward.cu:466.)  hx < 0 encodes "never contributes"; +inf encodes "never cull".
-__device__ __forceinline__ uint32_t warp_overlap_mask(float cx, float cy, float hx, float hy, float tile_x0, float tile_y0)
-{
-	const float lo_x = cx - hx, hi_x = cx + hx, lo_y = cy - hy, hi_y = cy + hy;
-	uint32_t mx = 0, my = 0;
-#pragma unroll
-	for (int i = 0; i < 2; i++) {
-		const float x0 = tile_x0 + 8.f * i;
-		if (hi_x >= x0 && lo_x <= x0 + 7.f) mx |= 1u << i;
-	}
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const float y0 = tile_y0 + 4.f * i;
-		if (hi_y >= y0 && lo_y <= y0 + 3.f) my |= 1u << i;
-	}
-	if (!(hx >= 0.f)) return 0; // negative extent: opacity < 1/255, alpha can never reach the threshold
-	uint32_t m = 0;
-#pragma unroll
-	for (int w = 0; w < 8; w++)
-		if (((mx >> (w & 1)) & 1u) && ((my >> (w >> 1)) & 1u)) m |= 1u << w;
-	return m;
-}
-
-// Build this warp's ordered list of staged Gaussians whose mask has the warp's bit set.
-// Returns the list length.  s_mask[kBatch] was written by all threads before a __syncthreads().
-__device__ __forceinline__ int build_warp_list(const uint8_t *s_mask, uint8_t *s_list_w, int warp, int lane, int count)
-{
-	int n = 0;
-#pragma unroll
-	for (int k = 0; k < kBatch / 32; k++) {
-		const int j = k * 32 + lane;
-		const bool hit = (j < count) && ((s_mask[j] >> warp) & 1u);
-		const uint32_t b = __ballot_sync(0xffffffffu, hit);
-		if (hit) s_list_w[n + __popc(b & ((1u << lane) - 1u))] = (uint8_t)j;
-		n += __popc(b);
-	}
-	__syncwarp();
-	return n;
 }
 
 } // namespace gsr

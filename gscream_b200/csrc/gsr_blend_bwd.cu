@@ -19,9 +19,9 @@
 //     COLUMN of its warp's 32 pixels in registers, the per-pixel weights alpha*T go through 128 B of
 //     shared memory, and the warp issues a single coalesced 128-B red.global.add per Gaussian.
 //     That is one RED instruction per (warp, Gaussian) where the reference issues 32 x C scalar atomics.
-//   * Same asynchronous double-buffered slab staging and per-warp bounding-box compaction as the forward
-//     kernel, plus a tile- and warp-level skip of everything behind the deepest last contributor, and a
-//     warp vote on a cheap necessary condition (power >= -log(255 opacity) - eps) before any exp is evaluated.
+//   * Same warp-private feed as the forward kernel (gsr_blend.cuh: per-warp list scan by the instance masks, private
+//     double-buffered cp.async gather, no block barrier), run back to front and started at the warp's own deepest last
+//     contributor — nothing behind it can receive gradient.
 //
 // Scalar terms are accumulated into gacc[P][8] = {dmean2D.x, dmean2D.y, dconic.x, dconic.y, dconic.w,
 // dopacity, ddepth, duncertainty}; colours into dL_dcolors[P][C].  Both must be zero (or hold the
@@ -29,17 +29,21 @@
 #include "gsr_blend.cuh"
 #include "gsr_internal.cuh"
 
-#ifndef GSR_BWD_EARLYVOTE
-#define GSR_BWD_EARLYVOTE 0
-#endif
 #ifndef GSR_BWD_RCP
 #define GSR_BWD_RCP 1
 #endif
 #ifndef GSR_BWD_ACC4
 #define GSR_BWD_ACC4 0
 #endif
+// C = 32: evaluate the two 32x32 products per (warp, chunk) on the tensor pipe (gsr_blend_bwd_mma.cu) instead of FFMA
+#ifndef GSR_BWD_MMA
+#define GSR_BWD_MMA 0
+#endif
 
 namespace gsr {
+
+constexpr int kWarpsPerCta = GSR_BWD_WARPS_PER_CTA;
+constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 
 // Transpose-reduce: every lane contributes N values; afterwards v[0] on lane l is the warp-wide total
 // of value index vidx<N>(l).  N/2 + N/4 + ... + 1 exchanges, then plain xor-adds for the remaining strides.
@@ -83,32 +87,24 @@ __device__ __forceinline__ bool vowner(int lane)
 #define GSR_BWD_MINBLOCKS(C) ((C) <= 8 ? 3 : 2)
 #endif
 template <int C>
-__global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kernel(
-    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int W, int H, int tiles_x,
+__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINBLOCKS(C) * kCtasPerTile) blend_backward_kernel(
+    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dpixel_uncs,
     float *__restrict__ gacc, float *__restrict__ dL_dcolors)
 {
 	using TR = BlendTraits<C>;
-	constexpr bool kBulk = GSR_BWD_BULK != 0;
 	constexpr bool kLaneChannel = (C == 32); // colour sums by role switch; otherwise through the butterfly
 	constexpr int NV = kLaneChannel ? 8 : 16;
 	static_assert(kLaneChannel || C <= 8, "butterfly path carries at most 8 colour channels");
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	uint32_t *s_ids = reinterpret_cast<uint32_t *>(smem_raw + TR::kIdsOff);  // [3][kBatch]
-	uint8_t *s_mask = smem_raw + TR::kMaskOff;                               // [3][kBatch]
-	uint8_t *s_list = smem_raw + TR::kListOff;                               // [8][kBatch]
-	auto stage_rec = [&](int s) { return reinterpret_cast<float *>(smem_raw + (size_t)s * TR::kStageBytes); };
-	auto stage_feat = [&](int s) { return reinterpret_cast<float *>(smem_raw + (size_t)s * TR::kStageBytes + (size_t)kBatch * GSR_REC_BYTES); };
-	__shared__ __align__(16) float s_w[kWarpsPerTile][32];
-	__shared__ int s_red[kWarpsPerTile];
+	__shared__ __align__(16) float s_w[kWarpsPerCta][32];
 
-	__shared__ __align__(8) uint64_t s_bar[kStages];
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int tile = blockIdx.x;
-	stage_init<C, kBulk>(s_bar, tid);
+	const int tid = threadIdx.x, lwarp = tid >> 5, lane = tid & 31;
+	const int tile = blockIdx.x / kCtasPerTile;
+	const int warp = (blockIdx.x % kCtasPerTile) * kWarpsPerCta + lwarp; // this warp's 8x4 pixel block within the tile
 	const int tile_x0 = (tile % tiles_x) * GSR_BLOCK_X, tile_y0 = (tile / tiles_x) * GSR_BLOCK_Y;
 	int bx, by;
 	warp_block_origin(warp, bx, by);
@@ -122,18 +118,12 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 	const float T_final = inside ? final_Ts[pix_id] : 0.f;
 	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
 
-	// deepest last contributor of the warp / of the tile: nothing behind it can receive gradient
+	// deepest last contributor of the warp: nothing behind it can receive gradient from these 32 pixels
 	int warp_last = last_contributor;
 #pragma unroll
 	for (int s = 16; s >= 1; s >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, s));
-	if (lane == 0) s_red[warp] = warp_last;
-	__syncthreads();
-	int total = 0;
-#pragma unroll
-	for (int w = 0; w < kWarpsPerTile; w++) total = max(total, s_red[w]);
-	total = min(total, (int)(range.y - range.x));
-	if (total == 0) return;
-	const int rounds = (total + kBatch - 1) / kBatch;
+	warp_last = min(warp_last, (int)(range.y - range.x));
+	if (warp_last == 0) return; // warps are independent: no barrier follows
 
 	// this pixel's upstream gradient row (colour channels, depth, uncertainty)
 	float g[C];
@@ -176,69 +166,25 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 	const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
 	const float neg_Tfinal_bg = -T_final * bg_dot; // background term: (-T_final / (1 - alpha)) * sum_ch bg[ch] g[ch]
 
-	// staged slot t of batch b holds list position total-1-(b*kBatch+t): back to front (CR/backward.cu:500)
-	auto load_id = [&](int b) -> uint32_t {
-		const int i = b * kBatch + tid;
-		return (tid < kBatch && i < total) ? point_list[range.x + (uint32_t)(total - 1 - i)] : 0u;
-	};
-	auto phase1 = [&](int b, uint32_t id) {
-		const int base = b * kBatch;
-		uint32_t mask = 0;
-		if (tid < kBatch) {
-			if (base + tid < total) {
-				const float *src = rec + (size_t)id * GSR_REC_FLOATS;
-				const float2 cxy = __ldg(reinterpret_cast<const float2 *>(src));
-				const float2 ext = __ldg(reinterpret_cast<const float2 *>(src + 8));
-				mask = warp_overlap_mask(cxy.x, cxy.y, ext.x, ext.y, (float)tile_x0, (float)tile_y0);
-				// per-warp: positions at or behind the warp's deepest last contributor cannot contribute
-				const int pos = total - 1 - (base + tid);
-#pragma unroll
-				for (int w = 0; w < kWarpsPerTile; w++)
-					if (pos >= s_red[w]) mask &= ~(1u << w);
-				s_ids[(b % kIdStages) * kBatch + tid] = id;
-			}
-			s_mask[(b % kIdStages) * kBatch + tid] = (uint8_t)mask;
-		}
-	};
-
-	uint32_t next_id = load_id(0);
-	phase1(0, next_id);
-	__syncthreads();
-	stage_issue<C, kBulk>(&s_bar[0], stage_rec(0), stage_feat(0), s_ids, next_id, min(kBatch, total), rec, features, tid);
-	next_id = load_id(1);
-
-	for (int r = 0; r < rounds; r++) {
-		if (r + 1 < rounds) phase1(r + 1, next_id);
-		stage_wait<kBulk>(&s_bar[r & 1], r >> 1);
-		__syncthreads(); // batch r landed, ids of batch r+1 visible, previous batch fully consumed
-		if (r + 1 < rounds)
-			stage_issue<C, kBulk>(&s_bar[(r + 1) & 1], stage_rec((r + 1) & 1), stage_feat((r + 1) & 1), s_ids + ((r + 1) % kIdStages) * kBatch, next_id,
-			               min(kBatch, total - (r + 1) * kBatch), rec, features, tid);
-		next_id = load_id(r + 2);
-
-		const int base = r * kBatch;
-		const int count = min(kBatch, total - base);
-		const float *s_rec = stage_rec(r & 1);
-		const float *s_feat = stage_feat(r & 1);
-		const uint32_t *ids = s_ids + (r % kIdStages) * kBatch;
-		uint8_t *my_list = s_list + warp * kBatch;
-		const int n = build_warp_list(s_mask + (r % kIdStages) * kBatch, my_list, warp, lane, count);
-
-		for (int k = 0; k < n; k++) {
-			const int j = my_list[k];
-			const int pos = total - 1 - (base + j); // 0-based list position
-			const float4 r0 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS);     // x y a b
-			const float4 r1 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 4); // c o depth unc
+	// back to front (CR/backward.cu:500): the feed scans list positions warp_last-1 .. 0
+	WarpFeed<C, true> feed;
+	feed.init(smem_raw + (size_t)lwarp * TR::kWarpBytes, point_list + range.x, warp_last, rec, features, warp, lane, packed != 0);
+	feed.fill();
+	int m_cur = feed.issue(0);
+	for (int chunk = 0; m_cur > 0; chunk++) {
+		feed.fill();
+		const int m_next = feed.issue((chunk + 1) & 1);
+		cp_async_wait_but_one();
+		__syncwarp(); // every lane's copies of this chunk have landed
+		const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
+		for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats) {
+			const uint32_t slot = (feed.done + e) & (kRing - 1);
+			const int pos = (int)feed.q_pos[slot]; // 0-based list position
+			const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
+			const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
 			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
 			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
-			// cheap necessary condition first: alpha = min(.99, o*exp(power)) >= 1/255 needs power >= -log(255 o) - eps
-			// (r[14], written by preprocess with a safety margin); most culled-in-vain iterations stop here, before exp
-#if GSR_BWD_EARLYVOTE
-			const bool maybe = (pos < last_contributor) && !(power > 0.0f) && (power >= s_rec[j * GSR_REC_FLOATS + 14]);
-			if (!__any_sync(0xffffffffu, maybe)) continue;
-#else
 			const bool maybe = (pos < last_contributor) && !(power > 0.0f);
-#endif
 			const float G = expf(power);
 			const float alpha = min(0.99f, __fmul_rn(r1.y, G));
 			const bool valid = maybe && !(alpha < kAlphaMin);
@@ -259,8 +205,7 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 				T = __fdiv_rn(T, one_minus);
 #endif
 				w = alpha * T;
-				// dot = f_j . g_p over colour channels, depth and uncertainty; four independent partial sums so the
-				// FMA latency chain is 1/4 as long
+				// dot = f_j . g_p over colour channels, depth and uncertainty
 #if GSR_BWD_ACC4
 				float d0 = r1.z * gd, d1 = r1.w * gu, d2 = 0.f, d3 = 0.f;
 #else
@@ -268,13 +213,13 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 				float &d1 = d0, &d2 = d0, &d3 = d0;
 #endif
 				if (TR::kFeatInRec) {
-					const float4 r2 = *reinterpret_cast<const float4 *>(s_rec + j * GSR_REC_FLOATS + 8);
-					const float cb = s_rec[j * GSR_REC_FLOATS + 12];
+					const float4 r2 = *reinterpret_cast<const float4 *>(ent + 8);
+					const float cb = ent[12];
 					if (C > 0) d2 += r2.z * g[0];
 					if (C > 1) d3 += r2.w * g[1 % C];
 					if (C > 2) d0 += cb * g[2 % C];
 				} else {
-					const float4 *f4 = reinterpret_cast<const float4 *>(s_feat + j * C);
+					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
 #pragma unroll
 					for (int q = 0; q < C / 4; q++) {
 						const float4 f = f4[q];
@@ -316,7 +261,7 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 					for (int ch = 0; ch < C; ch++) v[8 + ch] = w * g[ch];
 				}
 			}
-			const uint32_t id = ids[j];
+			const uint32_t id = feed.q_id[slot];
 
 			warp_transpose_reduce<NV>(v, lane);
 			if (vowner<NV>(lane)) {
@@ -325,7 +270,7 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 				else if (q < 8 + C) red_add(dL_dcolors + (size_t)id * C + (q - 8), v[0]);
 			}
 			if (kLaneChannel) {
-				s_w[warp][lane] = w;
+				s_w[lwarp][lane] = w;
 				__syncwarp();
 #if GSR_BWD_ACC4
 				float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -333,7 +278,7 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 				float s0 = 0.f;
 				float &s1 = s0, &s2 = s0, &s3 = s0;
 #endif
-				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[warp]);
+				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[lwarp]);
 #pragma unroll
 				for (int q = 0; q < 8; q++) {
 					const float4 ww = w4[q];
@@ -350,12 +295,15 @@ __global__ void __launch_bounds__(256, GSR_BWD_MINBLOCKS(C)) blend_backward_kern
 				__syncwarp();
 			}
 		}
+		feed.done += m_cur;
+		__syncwarp(); // the stage buffer and the ring slots of this chunk may be reused
+		m_cur = m_next;
 	}
-	stage_drain<kBulk>();
+	cp_async_wait_all();
 }
 
 template <int C>
-static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, int W, int H, int tiles_x, const float *rec,
+static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
                               const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                               const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                               float *dL_dcolors, cudaStream_t stream)
@@ -363,17 +311,17 @@ static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *po
 	using TR = BlendTraits<C>;
 	static bool configured = false;
 	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR::kSmemBytes);
+		cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t)kWarpsPerCta * TR::kWarpBytes);
 		if (e != cudaSuccess) return e;
 		configured = true;
 	}
-	blend_backward_kernel<C><<<tiles, 256, TR::kSmemBytes, stream>>>(ranges, point_list, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
+	blend_backward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * TR::kWarpBytes, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
 	                                                                dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
 	count_launch();
 	return cudaGetLastError();
 }
 
-cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
                                   const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                                   const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                                   float *dL_dcolors, cudaStream_t stream)
@@ -381,9 +329,14 @@ cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, cons
 	const int tiles_x = (W + GSR_BLOCK_X - 1) / GSR_BLOCK_X, tiles_y = (H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
 	const int tiles = tiles_x * tiles_y;
 	if (tiles <= 0) return cudaSuccess;
+	const int packed = point_list_packed(P) ? 1 : 0;
+#if GSR_BWD_MMA
+	if (C == 32)
+		return launch_blend_backward_mma(P, W, H, ranges, point_list, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+#endif
 	switch (C) {
-	case 3: return launch_bwd<3>(tiles, ranges, point_list, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
-	case 32: return launch_bwd<32>(tiles, ranges, point_list, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+	case 3: return launch_bwd<3>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+	case 32: return launch_bwd<32>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
 	default: return cudaErrorInvalidValue;
 	}
 }

@@ -72,6 +72,35 @@ __device__ __forceinline__ void get_rect(float px, float py, int max_radius, int
 	y1 = min(gy, max(0, (int)((py + max_radius + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y)));
 }
 
+// One bit per warp of a tile's CTA (warp w owns the 8x4 pixel block at x = 8 (w & 1), y = 4 (w >> 1)): does the bounding
+// box {|x - cx| <= hx, |y - cy| <= hy} of the Gaussian's alpha >= 1/255 region touch that block?  (Pixel centres are
+// integer coordinates, CR/forward.cu:466.)  hx < 0 encodes "never contributes"; +inf encodes "never cull".
+__device__ __forceinline__ uint32_t warp_overlap_mask(float cx, float cy, float hx, float hy, float tile_x0, float tile_y0)
+{
+	const float lo_x = cx - hx, hi_x = cx + hx, lo_y = cy - hy, hi_y = cy + hy;
+	uint32_t mx = 0, my = 0;
+#pragma unroll
+	for (int i = 0; i < 2; i++) {
+		const float x0 = tile_x0 + 8.f * i;
+		if (hi_x >= x0 && lo_x <= x0 + 7.f) mx |= 1u << i;
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const float y0 = tile_y0 + 4.f * i;
+		if (hi_y >= y0 && lo_y <= y0 + 3.f) my |= 1u << i;
+	}
+	if (!(hx >= 0.f)) return 0; // negative extent: opacity < 1/255, alpha can never reach the threshold
+	uint32_t m = 0;
+#pragma unroll
+	for (int w = 0; w < 8; w++)
+		if (((mx >> (w & 1)) & 1u) && ((my >> (w >> 1)) & 1u)) m |= 1u << w;
+	return m;
+}
+
+// point_list entries carry that mask in their top byte when every Gaussian id fits 24 bits (P <= 2^24); above that the
+// entries are plain ids and the blend kernels treat every instance as a candidate for every warp (still exact, slower).
+__host__ __device__ inline bool point_list_packed(int P) { return P <= (1 << 24); }
+
 // mbarrier + bulk-async (TMA, non-tensor form: SASS UBLKCP) wrappers, sm_90+/sm_100a.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
