@@ -344,8 +344,8 @@ def run_reference(args, cfg, rank, world, local):
 
 def run_train_step(args, rank, world, local):
     """BASELINE.json configs[3] substitute (SURVEY.md 8d "Config 4"): the train-step-equivalent loop of tests/_train_step.py,
-    1 GPU.  `--impl ours`: fused CUDA decode + this repo's rasterizer; `--impl reference`: torch decode (the reference's
-    generate_neural_gaussians restated) + the reference's own rasterizer build.  Losses / Adam are plain torch in both."""
+    1 GPU.  `--impl ours`: fused CUDA decode + this repo's rasterizer + fused L1/SSIM loss; `--impl reference`: torch decode (the reference's
+    generate_neural_gaussians restated) + the reference's own rasterizer build.  The aligned-depth loss and Adam are plain torch in both."""
     if rank != 0:
         return None
     import _train_step as ts
@@ -360,7 +360,7 @@ def run_train_step(args, rank, world, local):
     else:
         from gscream_b200 import rasterizer as mod
         dec = ts.fused_decode
-    loop = ts.TrainStep(mod, dec, A=A, k=k, W=W, H=H, device=dev)
+    loop = ts.TrainStep(mod, dec, A=A, k=k, W=W, H=H, device=dev, fused_losses=(args.impl == "ours"))
     ms, clocks = _timed(loop.step, args.steps, args.warmup, 1, ClockSampler(local))
     ms_per_step = ms / args.steps
     out = {"metric": "train-step-equivalent iters/sec", "value": 1000.0 / ms_per_step, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
@@ -369,7 +369,8 @@ def run_train_step(args, rank, world, local):
            "config": {"workload": "config4 substitute: %d anchors x %d offsets, %dx%d, prefilter + decode + rasterize (RGB+depth+uncertainty) + "
                                   "L1/SSIM/aligned-depth losses + Adam; P = %d Gaussians from %d visible anchors" % (A, k, W, H, loop.last["P"], loop.last["n_vis"]),
                       "decode": "fused CUDA (gsr_decode_*)" if args.impl == "ours" else "torch eager (reference code path)",
-                      "rasterizer": "libgsr_b200" if args.impl == "ours" else "reference CUDA build (oracle/_ref/dgr3)"},
+                      "rasterizer": "libgsr_b200" if args.impl == "ours" else "reference CUDA build (oracle/_ref/dgr3)",
+                      "losses": "fused L1 + SSIM (gsr_l1_ssim_*), eager aligned-depth loss and Adam" if args.impl == "ours" else "torch eager"},
            "clocks": clocks}
     if args.impl == "reference":
         out["impl"] = "reference"

@@ -6,6 +6,7 @@
 #include "../../include/gsr_b200.h"
 #include "gsr_internal.cuh"
 #include "gsr_decode.cuh"
+#include "gsr_loss.cuh"
 #include <atomic>
 
 namespace gsr {
@@ -17,7 +18,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // When enabled, every stage launch is bracketed by a cudaEvent pair on the caller's stream (a ring of
 // kProfCap pairs per stage).  Nothing is synchronised here; gsr_profile_read() is called after the
 // caller's own synchronise.  Disabled (the default) it costs one branch per stage.
-enum Stage { kPre = 0, kDepthScan, kBin, kBlendFwd, kBlendBwd, kPreBwd, kDecodeFwd, kDecodeBwd, kNumStages };
+enum Stage { kPre = 0, kDepthScan, kBin, kBlendFwd, kBlendBwd, kPreBwd, kDecodeFwd, kDecodeBwd, kLossFwd, kLossBwd, kNumStages };
 static constexpr int kProfCap = 256;
 static bool g_prof_on = false;
 static cudaEvent_t g_ev[kNumStages][kProfCap][2];
@@ -392,6 +393,34 @@ int gsr_decode_backward(int A, int feat_dim, int n_offsets, int64_t n_vis, int64
 	b.g_anchor = g_anchor; b.g_feat = g_feat; b.g_offset = g_offset; b.g_scaling = g_scaling;
 	StageTimer t(kDecodeBwd, stream);
 	GSR_CUDA(decode_backward(b, stream));
+	return 0;
+}
+
+// ---- fused L1 + SSIM image loss -------------------------------------------------------------------------------------------
+int gsr_l1_ssim_forward(int planes, int height, int width, const float *taps11_host, const float *image, const float *target,
+                        const float *mask, int mask_planes, double *sums, float *partials, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (planes <= 0 || height <= 0 || width <= 0 || !taps11_host || !image || !target || !sums) return GSR_E_BADARG;
+	if (mask && mask_planes != 1 && mask_planes != planes) return GSR_E_BADARG;
+	const size_t n = (size_t)planes * height * width;
+	StageTimer t(kLossFwd, stream);
+	GSR_CUDA(launch_l1_ssim_forward(planes, height, width, taps11_host, image, target, mask, mask_planes, sums, partials,
+	                                partials ? partials + n : nullptr, partials ? partials + 2 * n : nullptr, stream));
+	return 0;
+}
+
+int gsr_l1_ssim_backward(int planes, int height, int width, const float *taps11_host, const float *image, const float *target,
+                         const float *mask, int mask_planes, const float *partials, const float *upstream, float *grad_image,
+                         gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (planes <= 0 || height <= 0 || width <= 0 || !taps11_host || !image || !target || !partials || !upstream || !grad_image) return GSR_E_BADARG;
+	if (mask && mask_planes != 1 && mask_planes != planes) return GSR_E_BADARG;
+	const size_t n = (size_t)planes * height * width;
+	StageTimer t(kLossBwd, stream);
+	GSR_CUDA(launch_l1_ssim_backward(planes, height, width, taps11_host, image, target, mask, mask_planes, partials, partials + n,
+	                                 partials + 2 * n, upstream, grad_image, stream));
 	return 0;
 }
 

@@ -72,9 +72,7 @@ struct WarpFeed {
 	uint32_t tail, issued, done;
 	uint32_t pre0a, pre0b, pre1a, pre1b;  // entries of the next two scan steps (two per lane each)
 	int warp, lane;
-	int lane_e, lane_part;     // gather role of this lane: entry offset within a group of kGroup entries, 16-B part (or -1: idle)
 	bool packed;
-	static constexpr int kGroup = 32 / TR::kParts;  // entries gathered per warp-wide cp.async round
 
 	__device__ __forceinline__ int pos_of(int ordinal) const { return kReverse ? n - 1 - ordinal : ordinal; }
 	__device__ __forceinline__ uint32_t load_entry(int ordinal) const { return ordinal < n ? __ldg(list + pos_of(ordinal)) : 0u; }
@@ -86,8 +84,6 @@ struct WarpFeed {
 		q_id = reinterpret_cast<uint32_t *>(warp_smem + 2 * TR::kStageFloats * 4);
 		q_pos = q_id + kRing;
 		list = list_; n = n_; rec = rec_; feat = feat_; warp = warp_; lane = lane_; packed = packed_;
-		lane_e = lane / TR::kParts;
-		lane_part = lane_e < kGroup ? lane - lane_e * TR::kParts : -1;
 		next_scan = 0;
 		tail = issued = done = 0;
 		pre0a = load_entry(lane); pre0b = load_entry(32 + lane);
@@ -123,18 +119,34 @@ struct WarpFeed {
 		while ((int)(tail - issued) < 2 * kChunk && !exhausted()) refill();
 		__syncwarp();
 	}
-	// gather the next (up to) kChunk ring entries into stage buffer `s`; always commits one cp.async group
+	// gather the next (up to) kChunk ring entries into stage buffer `s`; always commits one cp.async group.
+	// Two uniform passes (records, then feature rows) with power-of-two lane -> (entry, 16-B part) maps, so that a round is
+	// LDS id / LEA / LDGSTS: a single mixed pass cost 32 instructions per round in index and base-pointer selection
+	// (12.7 % of the forward kernel's instructions, profiles/r1_blend_v5_summary.md).
 	__device__ __forceinline__ int issue(int s)
 	{
 		const int m = min(kChunk, (int)(tail - issued));
 		float *dst = stage + s * TR::kStageFloats;
-		// lane -> (entry e0 + lane_e, part lane_part): kGroup entries per round, no index arithmetic in the loop
-		const bool is_rec = lane_part < TR::kRecParts;
-		const float *base = is_rec ? rec + lane_part * 4 : feat + (lane_part - TR::kRecParts) * 4;
-		const uint32_t stride = is_rec ? GSR_REC_FLOATS : C;
-		float *d = dst + lane_e * TR::kEntryFloats + lane_part * 4;
-		for (int e = lane_e; e < m; e += kGroup, d += kGroup * TR::kEntryFloats) {
-			if (lane_part >= 0) cp_async16(d, base + (size_t)q_id[(issued + e) & (kRing - 1)] * stride);
+		{
+			constexpr int kPer = 32 / TR::kRecParts; // entries per round
+			const int le = lane / TR::kRecParts, part = lane % TR::kRecParts;
+#pragma unroll
+			for (int r = 0; r < kChunk / kPer; r++) {
+				const int e = r * kPer + le;
+				if (e < m)
+					cp_async16(dst + e * TR::kEntryFloats + part * 4, rec + (size_t)q_id[(issued + e) & (kRing - 1)] * GSR_REC_FLOATS + part * 4);
+			}
+		}
+		if constexpr (!TR::kFeatInRec) {
+			constexpr int kPer = 32 / TR::kFeatParts;
+			static_assert(32 % TR::kFeatParts == 0, "feature row must split into a power-of-two number of 16-B parts");
+			const int le = lane / TR::kFeatParts, part = lane % TR::kFeatParts;
+#pragma unroll
+			for (int r = 0; r < kChunk / kPer; r++) {
+				const int e = r * kPer + le;
+				if (e < m)
+					cp_async16(dst + e * TR::kEntryFloats + (TR::kRecParts + part) * 4, feat + (size_t)q_id[(issued + e) & (kRing - 1)] * C + part * 4);
+			}
 		}
 		cp_async_commit();
 		issued += m;

@@ -39,6 +39,11 @@
 #ifndef GSR_BWD_MMA
 #define GSR_BWD_MMA 0
 #endif
+// C = 32: keep the lane = channel copy of the gradient block (the column each lane needs for the colour sums) in shared
+// memory instead of 32 registers per lane: ~96 registers -> 20 warps per SM instead of 16, for 8 more LDS.128 per pair
+#ifndef GSR_BWD_GCOL_SMEM
+#define GSR_BWD_GCOL_SMEM 0
+#endif
 
 namespace gsr {
 
@@ -86,8 +91,16 @@ __device__ __forceinline__ bool vowner(int lane)
 #ifndef GSR_BWD_MINBLOCKS
 #define GSR_BWD_MINBLOCKS(C) ((C) <= 8 ? 3 : 2)
 #endif
+#if GSR_BWD_GCOL_SMEM
+#ifndef GSR_BWD_GCOL_WARPS
+#define GSR_BWD_GCOL_WARPS 20
+#endif
+#define GSR_BWD_MINCTAS(C) ((C) == 32 ? (GSR_BWD_GCOL_WARPS / kWarpsPerCta) : GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
+#else
+#define GSR_BWD_MINCTAS(C) (GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
+#endif
 template <int C>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINBLOCKS(C) * kCtasPerTile) blend_backward_kernel(
+__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_backward_kernel(
     const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
@@ -96,6 +109,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINBLOCKS(C) * kCta
 {
 	using TR = BlendTraits<C>;
 	constexpr bool kLaneChannel = (C == 32); // colour sums by role switch; otherwise through the butterfly
+	constexpr bool kGcolSmem = kLaneChannel && (GSR_BWD_GCOL_SMEM != 0);
+	constexpr int kGcolStride = 36;
 	constexpr int NV = kLaneChannel ? 8 : 16;
 	static_assert(kLaneChannel || C <= 8, "butterfly path carries at most 8 colour channels");
 
@@ -138,8 +153,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINBLOCKS(C) * kCta
 		gu = dL_dpixel_uncs[pix_id];
 	}
 	// role switch (C == 32): lane l also holds channel l's gradient for the warp's 32 pixels
-	float gcol[kLaneChannel ? 32 : 1];
-	if (kLaneChannel) {
+	float gcol[(kLaneChannel && !kGcolSmem) ? 32 : 1];
+	float *s_gc = reinterpret_cast<float *>(smem_raw + (size_t)kWarpsPerCta * TR::kWarpBytes) + lwarp * 32 * kGcolStride; // [ch][36]
+	if (kGcolSmem) {
+#pragma unroll
+		for (int ch = 0; ch < C; ch++) s_gc[ch * kGcolStride + lane] = g[ch];
+		__syncwarp();
+	} else if (kLaneChannel) {
 		const float *src = dL_dpixels + (size_t)lane * plane;
 		const int x0 = tile_x0 + bx, y0 = tile_y0 + by;
 		const bool vec_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0) && (x0 + 8 <= W);
@@ -279,13 +299,22 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINBLOCKS(C) * kCta
 				float &s1 = s0, &s2 = s0, &s3 = s0;
 #endif
 				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[lwarp]);
+				const float4 *c4 = reinterpret_cast<const float4 *>(s_gc + lane * kGcolStride);
 #pragma unroll
 				for (int q = 0; q < 8; q++) {
 					const float4 ww = w4[q];
-					s0 += ww.x * gcol[4 * q + 0];
-					s1 += ww.y * gcol[4 * q + 1];
-					s2 += ww.z * gcol[4 * q + 2];
-					s3 += ww.w * gcol[4 * q + 3];
+					if (kGcolSmem) {
+						const float4 gc = c4[q];
+						s0 += ww.x * gc.x;
+						s1 += ww.y * gc.y;
+						s2 += ww.z * gc.z;
+						s3 += ww.w * gc.w;
+					} else {
+						s0 += ww.x * gcol[(4 * q + 0) % (kGcolSmem ? 1 : 32)];
+						s1 += ww.y * gcol[(4 * q + 1) % (kGcolSmem ? 1 : 32)];
+						s2 += ww.z * gcol[(4 * q + 2) % (kGcolSmem ? 1 : 32)];
+						s3 += ww.w * gcol[(4 * q + 3) % (kGcolSmem ? 1 : 32)];
+					}
 				}
 #if GSR_BWD_ACC4
 				red_add(dL_dcolors + (size_t)id * C + lane, (s0 + s1) + (s2 + s3)); // 32 lanes -> one coalesced 128-B RED
@@ -303,6 +332,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINBLOCKS(C) * kCta
 }
 
 template <int C>
+static size_t bwd_smem_bytes()
+{
+	return (size_t)kWarpsPerCta * (BlendTraits<C>::kWarpBytes + ((C == 32 && GSR_BWD_GCOL_SMEM) ? 32 * 36 * 4 : 0));
+}
+
+template <int C>
 static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
                               const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                               const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
@@ -311,11 +346,11 @@ static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *po
 	using TR = BlendTraits<C>;
 	static bool configured = false;
 	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t)kWarpsPerCta * TR::kWarpBytes);
+		cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes<C>());
 		if (e != cudaSuccess) return e;
 		configured = true;
 	}
-	blend_backward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * TR::kWarpBytes, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
+	blend_backward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, bwd_smem_bytes<C>(), stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
 	                                                                dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
 	count_launch();
 	return cudaGetLastError();

@@ -1,0 +1,200 @@
+// gsr_loss.cu — fused image loss L1 + SSIM (forward and backward), SURVEY.md section 8f rank 3.
+//
+// Replaces, for the photometric term of train.py:535-545 of W-Ted/GScream,
+//     l1_loss / l1_loss_masked            utils/loss_utils.py:27-31
+//     ssim / _ssim, ssim_masked / _ssim_masked   utils/loss_utils.py:131-207
+// i.e. five depthwise 11x11 Gaussian convolutions (of x, y, x^2, y^2, xy), ~15 elementwise kernels and two reductions in the
+// forward and about twice that in the backward, by one kernel each way:
+//   forward : per 16x16 output tile of one image plane, stage the 26x26 halo of x (rendered) and y (target) in shared memory,
+//             run the Gaussian window separably (11 taps horizontally on 26 rows, then 11 taps vertically), evaluate the SSIM
+//             map and |x - y|, weight both by the optional mask, block-reduce and add to two fp64 accumulators; keep the three
+//             partial-derivative planes dm/dmu1, dm/d(conv x^2), dm/d(conv xy) (times the mask) for the backward.
+//   backward: convolve the three planes with the same (symmetric, zero-padded => self-adjoint) window and combine:
+//             dL/dx = g_ssim/N * (conv(p1) + 2 x conv(p2) + y conv(p3)) + g_l1/N * sign(x - y) * mask.
+// The window is separable by construction (create_window: outer product of the normalised 1-D Gaussian, loss_utils.py:116-121);
+// the 11 taps come from the host, computed exactly as the reference computes them (fp32).
+// HBM-bound by design: forward reads 2 planes and writes 3, backward reads 5 (+mask) and writes 1; ~150 FMA per pixel.
+#include "gsr_internal.cuh"
+#include "gsr_loss.cuh"
+
+namespace gsr {
+
+namespace {
+
+constexpr int kT = 16;          // output tile edge
+constexpr int kR = 5;           // window radius (window_size 11)
+constexpr int kTH = kT + 2 * kR; // 26: tile + halo
+
+struct Taps { float g[2 * kR + 1]; };
+
+__device__ __forceinline__ double block_sum_256(float v, float *s_red /*[8]*/)
+{
+#pragma unroll
+	for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+	const int tid = threadIdx.y * kT + threadIdx.x;
+	if ((tid & 31) == 0) s_red[tid >> 5] = v;
+	__syncthreads();
+	double t = 0.0;
+	if (tid == 0)
+		for (int w = 0; w < 8; w++) t += (double)s_red[w];
+	__syncthreads();
+	return t; // valid on thread 0
+}
+
+__global__ void __launch_bounds__(256) l1_ssim_forward_kernel(int H, int W, Taps taps, const float *__restrict__ x, const float *__restrict__ y,
+                                                              const float *__restrict__ mask, int mask_planes, double *__restrict__ sums,
+                                                              float *__restrict__ p1, float *__restrict__ p2, float *__restrict__ p3)
+{
+	__shared__ float sx[kTH][kTH + 1], sy[kTH][kTH + 1];
+	__shared__ float hc[5][kTH][kT];
+	__shared__ float s_red[8];
+	const int plane = blockIdx.z;
+	const size_t pbase = (size_t)plane * H * W;
+	const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
+	const int tid = threadIdx.y * kT + threadIdx.x;
+	for (int i = tid; i < kTH * kTH; i += 256) {
+		const int r = i / kTH, c = i - r * kTH;
+		const int gy = y0 + r - kR, gx = x0 + c - kR;
+		const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W; // zero padding (padding = window_size // 2)
+		sx[r][c] = in ? __ldg(x + pbase + (size_t)gy * W + gx) : 0.f;
+		sy[r][c] = in ? __ldg(y + pbase + (size_t)gy * W + gx) : 0.f;
+	}
+	__syncthreads();
+	for (int i = tid; i < kTH * kT; i += 256) {
+		const int r = i / kT, c = i - r * kT;
+		float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+#pragma unroll
+		for (int k = 0; k <= 2 * kR; k++) {
+			const float g = taps.g[k], u = sx[r][c + k], v = sy[r][c + k];
+			a = fmaf(g, u, a);
+			b = fmaf(g, v, b);
+			aa = fmaf(g, u * u, aa);
+			bb = fmaf(g, v * v, bb);
+			ab = fmaf(g, u * v, ab);
+		}
+		hc[0][r][c] = a; hc[1][r][c] = b; hc[2][r][c] = aa; hc[3][r][c] = bb; hc[4][r][c] = ab;
+	}
+	__syncthreads();
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	const int gx = x0 + tx, gy = y0 + ty;
+	float m_w = 0.f, l1_w = 0.f;
+	if (gx < W && gy < H) {
+		float mu1 = 0.f, mu2 = 0.f, cxx = 0.f, cyy = 0.f, cxy = 0.f;
+#pragma unroll
+		for (int k = 0; k <= 2 * kR; k++) {
+			const float g = taps.g[k];
+			mu1 = fmaf(g, hc[0][ty + k][tx], mu1);
+			mu2 = fmaf(g, hc[1][ty + k][tx], mu2);
+			cxx = fmaf(g, hc[2][ty + k][tx], cxx);
+			cyy = fmaf(g, hc[3][ty + k][tx], cyy);
+			cxy = fmaf(g, hc[4][ty + k][tx], cxy);
+		}
+		// utils/loss_utils.py:145-157
+		const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+		const float s1 = cxx - mu1_sq, s2 = cyy - mu2_sq, s12 = cxy - mu12;
+		const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+		const float A = 2.f * mu12 + C1, B = 2.f * s12 + C2, D = mu1_sq + mu2_sq + C1, E = s1 + s2 + C2;
+		const float inv_DE = 1.f / (D * E);
+		const float m = A * B * inv_DE;
+		const size_t pix = (size_t)gy * W + gx;
+		const float wm = mask ? __ldg(mask + (size_t)(mask_planes == 1 ? 0 : plane) * H * W + pix) : 1.f;
+		m_w = m * wm;
+		l1_w = fabsf(sx[ty + kR][tx + kR] - sy[ty + kR][tx + kR]) * wm;
+		if (p1) {
+			// total derivatives of m w.r.t. the three convolution outputs that depend on x: mu1, conv(x^2), conv(xy)
+			const float dm_dmu1 = 2.f * (mu2 * (B - A) * inv_DE + mu1 * m * (1.f / E - 1.f / D));
+			p1[pbase + pix] = dm_dmu1 * wm;
+			p2[pbase + pix] = -m / E * wm;
+			p3[pbase + pix] = 2.f * A * inv_DE * wm;
+		}
+	}
+	const double ts = block_sum_256(m_w, s_red);
+	if (tid == 0) atomicAdd(sums + 0, ts);
+	const double tl = block_sum_256(l1_w, s_red);
+	if (tid == 0) atomicAdd(sums + 1, tl);
+}
+
+__global__ void __launch_bounds__(256) l1_ssim_backward_kernel(int H, int W, Taps taps, const float *__restrict__ x, const float *__restrict__ y,
+                                                               const float *__restrict__ mask, int mask_planes, const float *__restrict__ p1,
+                                                               const float *__restrict__ p2, const float *__restrict__ p3,
+                                                               const float *__restrict__ upstream /*[2]: dL/d(ssim mean), dL/d(l1 mean)*/,
+                                                               float inv_n, float *__restrict__ dx)
+{
+	__shared__ float sp[3][kTH][kTH + 1];
+	__shared__ float hc[3][kTH][kT];
+	const int plane = blockIdx.z;
+	const size_t pbase = (size_t)plane * H * W;
+	const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
+	const int tid = threadIdx.y * kT + threadIdx.x;
+	for (int i = tid; i < kTH * kTH; i += 256) {
+		const int r = i / kTH, c = i - r * kTH;
+		const int gy = y0 + r - kR, gx = x0 + c - kR;
+		const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+		const size_t o = pbase + (size_t)gy * W + gx;
+		sp[0][r][c] = in ? __ldg(p1 + o) : 0.f;
+		sp[1][r][c] = in ? __ldg(p2 + o) : 0.f;
+		sp[2][r][c] = in ? __ldg(p3 + o) : 0.f;
+	}
+	__syncthreads();
+	for (int i = tid; i < kTH * kT; i += 256) {
+		const int r = i / kT, c = i - r * kT;
+		float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+		for (int k = 0; k <= 2 * kR; k++) {
+			const float g = taps.g[k];
+			a = fmaf(g, sp[0][r][c + k], a);
+			b = fmaf(g, sp[1][r][c + k], b);
+			d = fmaf(g, sp[2][r][c + k], d);
+		}
+		hc[0][r][c] = a; hc[1][r][c] = b; hc[2][r][c] = d;
+	}
+	__syncthreads();
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	const int gx = x0 + tx, gy = y0 + ty;
+	if (gx >= W || gy >= H) return;
+	float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+	for (int k = 0; k <= 2 * kR; k++) {
+		const float g = taps.g[k];
+		c1 = fmaf(g, hc[0][ty + k][tx], c1);
+		c2 = fmaf(g, hc[1][ty + k][tx], c2);
+		c3 = fmaf(g, hc[2][ty + k][tx], c3);
+	}
+	const size_t pix = (size_t)gy * W + gx;
+	const float xv = __ldg(x + pbase + pix), yv = __ldg(y + pbase + pix);
+	const float wm = mask ? __ldg(mask + (size_t)(mask_planes == 1 ? 0 : plane) * H * W + pix) : 1.f;
+	const float gs = __ldg(upstream) * inv_n, gl = __ldg(upstream + 1) * inv_n;
+	const float diff = xv - yv;
+	const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f); // torch.abs backward: sign(0) = 0
+	dx[pbase + pix] = gs * (c1 + 2.f * xv * c2 + yv * c3) + gl * sgn * wm;
+}
+
+} // namespace
+
+cudaError_t launch_l1_ssim_forward(int planes, int H, int W, const float *taps11, const float *x, const float *y, const float *mask,
+                                   int mask_planes, double *sums, float *p1, float *p2, float *p3, cudaStream_t stream)
+{
+	Taps t;
+	for (int k = 0; k < 11; k++) t.g[k] = taps11[k];
+	cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double), stream);
+	if (e != cudaSuccess) return e;
+	dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, planes), block(kT, kT);
+	l1_ssim_forward_kernel<<<grid, block, 0, stream>>>(H, W, t, x, y, mask, mask_planes, sums, p1, p2, p3);
+	count_launch(2);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_l1_ssim_backward(int planes, int H, int W, const float *taps11, const float *x, const float *y, const float *mask,
+                                    int mask_planes, const float *p1, const float *p2, const float *p3, const float *upstream, float *dx,
+                                    cudaStream_t stream)
+{
+	Taps t;
+	for (int k = 0; k < 11; k++) t.g[k] = taps11[k];
+	dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, planes), block(kT, kT);
+	l1_ssim_backward_kernel<<<grid, block, 0, stream>>>(H, W, t, x, y, mask, mask_planes, p1, p2, p3, upstream,
+	                                                   1.0f / ((float)planes * (float)H * (float)W), dx);
+	count_launch();
+	return cudaGetLastError();
+}
+
+} // namespace gsr

@@ -1,0 +1,17 @@
+// gsr_loss.cuh — declarations of the fused L1 + SSIM image loss (gsr_loss.cu), shared with gsr_api.cu.
+#pragma once
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+// x = rendered planes, y = target planes, both [planes][H][W]; mask [mask_planes][H][W] with mask_planes in {1, planes}, or null.
+// sums (device, fp64[2]) receives sum(ssim_map * mask) and sum(|x - y| * mask); p1..p3 (each [planes][H][W], or all null when no
+// backward will follow) the mask-weighted partial derivatives the backward convolves.  taps11: HOST pointer to the 11 window taps.
+cudaError_t launch_l1_ssim_forward(int planes, int H, int W, const float *taps11, const float *x, const float *y, const float *mask,
+                                   int mask_planes, double *sums, float *p1, float *p2, float *p3, cudaStream_t stream);
+// upstream (device, fp32[2]): dL/d(mean ssim), dL/d(mean l1).  dx [planes][H][W] is overwritten.
+cudaError_t launch_l1_ssim_backward(int planes, int H, int W, const float *taps11, const float *x, const float *y, const float *mask,
+                                    int mask_planes, const float *p1, const float *p2, const float *p3, const float *upstream, float *dx,
+                                    cudaStream_t stream);
+
+} // namespace gsr

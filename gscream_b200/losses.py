@@ -1,0 +1,110 @@
+"""Fused photometric losses: drop-ins for `l1_loss`, `l1_loss_masked`, `ssim`, `ssim_masked` of W-Ted/GScream's
+utils/loss_utils.py (:27-31, :131-207), SURVEY.md section 8f rank 3.
+
+Same names, argument order and return values (0-d tensors) as the reference functions, so train.py:535-545 can import them
+from here instead; `l1_ssim(image, gt, mask)` returns both means from ONE forward / ONE backward kernel
+(`gsr_l1_ssim_forward/backward` of include/gsr_b200.h), which is what the train-step loop of bench.py uses.
+Only the rendered image receives a gradient (the target and the mask are data).  No CPU / eager fallback: CPU tensors raise.
+"""
+from math import exp
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _taps(window_size=11, sigma=1.5):
+    """The reference's normalised 1-D window, computed the way it computes it (loss_utils.py:112-114: Python-float exp,
+    fp32 tensor, fp32 sum); its 2-D window is the outer product of this vector (loss_utils.py:116-121)."""
+    g = torch.Tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
+    return np.ascontiguousarray((g / g.sum()).numpy(), dtype=np.float32)
+
+
+_TAPS11 = _taps()
+
+
+def _planes(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError("%s must be a float32 CUDA tensor (got %s on %s); there is no CPU loss path" % (name, t.dtype, t.device))
+    if t.dim() < 2:
+        raise ValueError("%s must be [..., H, W]" % name)
+    t = t.contiguous()
+    H, W = t.shape[-2], t.shape[-1]
+    return t, int(t.numel() // (H * W)), int(H), int(W)
+
+
+class _L1SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, target, mask):
+        lib = _lib.load()
+        x, planes, H, W = _planes(image, "image")
+        y, planes_y, Hy, Wy = _planes(target, "target")
+        if (planes_y, Hy, Wy) != (planes, H, W):
+            raise ValueError("image and target shapes differ: %s vs %s" % (tuple(image.shape), tuple(target.shape)))
+        m, mp = None, 0
+        if mask is not None:
+            m, mp, Hm, Wm = _planes(mask.to(torch.float32) if mask.dtype != torch.float32 else mask, "mask")
+            if (Hm, Wm) != (H, W) or mp not in (1, planes):
+                raise ValueError("mask must broadcast over the image planes: %s vs %s" % (tuple(mask.shape), tuple(image.shape)))
+        dev = x.device
+        sums = torch.empty(2, dtype=torch.float64, device=dev)
+        need_grad = image.requires_grad
+        partials = torch.empty((3, planes, H, W), dtype=torch.float32, device=dev) if need_grad else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.gsr_l1_ssim_forward(planes, H, W, _TAPS11.ctypes.data, x.data_ptr(), y.data_ptr(),
+                                               m.data_ptr() if m is not None else None, mp, sums.data_ptr(),
+                                               partials.data_ptr() if partials is not None else None,
+                                               torch.cuda.current_stream().cuda_stream))
+        means = (sums / float(planes * H * W)).to(torch.float32)
+        ctx.save_for_backward(x, y, m if m is not None else torch.empty(0, device=dev), partials if partials is not None else torch.empty(0, device=dev))
+        ctx.dims = (planes, H, W, mp, tuple(image.shape))
+        return means[0], means[1]   # mean SSIM, mean L1
+
+    @staticmethod
+    def backward(ctx, g_ssim, g_l1):
+        lib = _lib.load()
+        x, y, m, partials = ctx.saved_tensors
+        planes, H, W, mp, shape = ctx.dims
+        if partials.numel() == 0:
+            raise RuntimeError("l1_ssim backward without a forward that saved its partials")
+        dev = x.device
+        ups = torch.stack([g_ssim.to(torch.float32).reshape(()), g_l1.to(torch.float32).reshape(())]).contiguous()
+        grad = torch.empty((planes, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gsr_l1_ssim_backward(planes, H, W, _TAPS11.ctypes.data, x.data_ptr(), y.data_ptr(),
+                                                m.data_ptr() if m.numel() else None, mp, partials.data_ptr(), ups.data_ptr(),
+                                                grad.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return grad.view(shape), None, None
+
+
+def l1_ssim(image, gt, mask=None):
+    """(mean SSIM, mean L1) of `image` against `gt`, both optionally weighted by `mask` exactly like ssim_masked /
+    l1_loss_masked (weights multiply the per-element maps, the mean still divides by the element count)."""
+    if gt.requires_grad or (mask is not None and mask.requires_grad):
+        raise NotImplementedError("fused l1_ssim differentiates w.r.t. the rendered image only")
+    return _L1SSIM.apply(image, gt, mask)
+
+
+def l1_loss(network_output, gt):
+    """utils/loss_utils.py:27-28."""
+    return l1_ssim(network_output, gt)[1]
+
+
+def l1_loss_masked(network_output, gt, mask):
+    """utils/loss_utils.py:30-31."""
+    return l1_ssim(network_output, gt, mask)[1]
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    """utils/loss_utils.py:131-164."""
+    if window_size != 11 or not size_average:
+        raise NotImplementedError("fused ssim supports window_size=11, size_average=True (the values train.py uses)")
+    return l1_ssim(img1, img2)[0]
+
+
+def ssim_masked(img1, img2, mask, window_size=11, size_average=True):
+    """utils/loss_utils.py:166-207."""
+    if window_size != 11 or not size_average:
+        raise NotImplementedError("fused ssim_masked supports window_size=11, size_average=True (the values train.py uses)")
+    return l1_ssim(img1, img2, mask)[0]

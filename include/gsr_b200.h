@@ -189,6 +189,27 @@ GSR_API int gsr_decode_backward(
     float *g_anchor, float *g_feat, float *g_offset, float *g_scaling, float *const *g_mlp_params, gsr_stream_t stream);
 
 /*
+ * Fused photometric loss, L1 + SSIM — replaces l1_loss / l1_loss_masked
+ * (utils/loss_utils.py:27-31) and ssim / ssim_masked (utils/loss_utils.py:131-207, 11x11 Gaussian window, sigma 1.5,
+ * zero padding, C1 = 0.01^2, C2 = 0.03^2, mean over all elements) as used by train.py:535-545.
+ *   image, target: [planes, H, W] (planes = batch x channels; the window is depthwise); mask: [mask_planes, H, W] with
+ *   mask_planes == 1 (broadcast) or == planes, or NULL; taps11_host: HOST pointer to the 11 fp32 taps of the normalised 1-D
+ *   window (the reference's 2-D window is their outer product, loss_utils.py:112-121).
+ * forward : sums (DEVICE fp64[2]) = { sum(ssim_map * mask), sum(|image - target| * mask) } — divide by planes*H*W for the
+ *           reference's means; partials (DEVICE fp32 [3, planes, H, W], or NULL if no backward follows) is scratch for
+ *           the backward.
+ * backward: upstream (DEVICE fp32[2]) = { dL/d(mean ssim), dL/d(mean l1) }; grad_image [planes, H, W] is overwritten.
+ */
+GSR_API int gsr_l1_ssim_forward(
+    int planes, int height, int width, const float *taps11_host,
+    const float *image, const float *target, const float *mask, int mask_planes,
+    double *sums, float *partials, gsr_stream_t stream);
+GSR_API int gsr_l1_ssim_backward(
+    int planes, int height, int width, const float *taps11_host,
+    const float *image, const float *target, const float *mask, int mask_planes,
+    const float *partials, const float *upstream, float *grad_image, gsr_stream_t stream);
+
+/*
  * Introspection for parity tests (device -> device copies out of the private scratch layout).
  * Any output pointer may be NULL.  Shapes: xy[P,2] depths[P] conic_opacity[P,4]
  * tiles_touched[P] point_list[R] ranges[tiles,2] final_T[H*W] n_contrib[H*W].
@@ -207,7 +228,8 @@ GSR_API int gsr_debug_export(
  * synchronised); gsr_profile_enable(0) stops.  After the caller has synchronised, gsr_profile_read() copies the
  * elapsed milliseconds of the recorded launches of one stage to HOST memory and returns how many there were.
  * Stages: 0 preprocess, 1 depth order + scan, 2 instance binning, 3 blend forward, 4 blend backward,
- * 5 per-Gaussian backward, 6 decode forward (stages 1 + 2), 7 decode backward.
+ * 5 per-Gaussian backward, 6 decode forward (stages 1 + 2), 7 decode backward,
+ * 8 L1+SSIM forward, 9 L1+SSIM backward.
  */
 GSR_API int gsr_profile_enable(int on);
 GSR_API int gsr_profile_read(int stage, float *ms_host, int capacity);

@@ -9,7 +9,8 @@ SURVEY.md section 8d "Config 4").  One iteration = what train.py:497-603 does ar
 
 on a synthetic anchor model (10^5 anchors x 10 offsets, 1008x567) with synthetic target image / depth.  Both arms run
 this same file; they differ only in `decode` (torch restatement vs gscream_b200.decode) and `rast` (reference build vs
-gscream_b200.rasterizer).  Losses and optimizer are plain torch on both sides (not yet fused).
+gscream_b200.rasterizer).  The reference arm's losses are eager torch (its own code path); this repo's arm uses the fused L1 + SSIM kernel
+(gscream_b200.losses); the depth-alignment loss and the optimizer are plain torch on both sides.
 """
 import math
 
@@ -53,9 +54,10 @@ def compute_scale_and_shift(prediction, target, mask):
 
 
 class TrainStep:
-    def __init__(self, rast_module, decode_fn, A=100000, k=10, W=1008, H=567, seed=4, device="cuda"):
+    def __init__(self, rast_module, decode_fn, A=100000, k=10, W=1008, H=567, seed=4, device="cuda", fused_losses=False):
         from gscream_b200 import scenes
         self.mod, self.decode_fn, self.dev = rast_module, decode_fn, torch.device(device)
+        self.fused_losses = fused_losses
         self.cam = scenes.make_camera(W, H)
         self.pc = ad.SyntheticAnchors(A, n_offsets=k, seed=seed, tanfov=(self.cam["tanfovx"], self.cam["tanfovy"])).to(self.dev)
         g = torch.Generator().manual_seed(seed + 1)
@@ -79,8 +81,13 @@ class TrainStep:
         ssp = torch.zeros_like(xyz, requires_grad=True)
         image, depth, uncer, radii = rast(means3D=xyz, means2D=ssp, shs=None, colors_precomp=color, opacities=opacity, uncertainties=unc,
                                           scales=scaling, rotations=rot, cov3D_precomp=None)
-        l1 = (image - self.target).abs().mean()
-        loss = 0.8 * l1 + 0.2 * (1.0 - ssim(image, self.target, self.window))
+        if self.fused_losses:
+            from gscream_b200 import losses
+            s_mean, l1 = losses.l1_ssim(image, self.target)            # one kernel each way (gsr_l1_ssim_*)
+            loss = 0.8 * l1 + 0.2 * (1.0 - s_mean)
+        else:
+            l1 = (image - self.target).abs().mean()
+            loss = 0.8 * l1 + 0.2 * (1.0 - ssim(image, self.target, self.window))
         s, t = compute_scale_and_shift(depth, self.target_depth, self.valid)
         aligned = s.abs().view(-1, 1, 1) * depth + t.view(-1, 1, 1)
         loss = loss + 0.1 * (aligned - self.target_depth).abs().mean()

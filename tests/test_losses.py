@@ -1,0 +1,104 @@
+"""Fused L1 + SSIM image loss (gscream_b200/losses.py + gsr_loss.cu).
+
+Oracle chain: tests/golden/loss_*.npz hold values and image gradients of the REFERENCE's own l1_loss / l1_loss_masked /
+ssim / ssim_masked (utils/loss_utils.py), executed from /root/reference by tests/golden/make_loss_golden.py in fp32 and
+fp64.  CPU tests pin the torch restatement used by bench.py's train-step loop (tests/_train_step.ssim) to them; GPU tests
+compare the CUDA path (through the C ABI) with the vectors and, at the train-step size, with the restatement in fp64.
+
+Tolerances: loss values |ours - ref64| <= 1e-5 * |ref64|; image gradients <= 1e-5 * max|ref64| (+ 2x the reference's own
+fp32-vs-fp64 difference).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _train_step as ts
+
+GOLDEN = ("loss_rgb", "loss_rgb_masked1", "loss_rgb_masked3", "loss_tiny")
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    mask = None if z["mask"].size == 0 else torch.from_numpy(z["mask"])
+    return z, torch.from_numpy(z["img"]), torch.from_numpy(z["gt"]), mask
+
+
+@pytest.mark.parametrize("name", ("loss_rgb", "loss_tiny"))
+def test_restatement_matches_reference_ssim(golden_dir, name):
+    z, img, gt, _ = _load(golden_dir, name)
+    x = img.clone().requires_grad_(True)
+    s = ts.ssim(x, gt, ts._gaussian_window(channels=img.shape[0]))
+    g, = torch.autograd.grad(s, x)
+    assert abs(float(s) - float(z["ssim"])) <= 1e-6
+    assert np.abs(g.numpy() - z["g_ssim"]).max() <= 1e-6 * max(np.abs(z["g_ssim"]).max(), 1e-9) + 1e-10
+
+
+def test_losses_fail_loudly_without_cuda_tensors():
+    from gscream_b200 import losses
+    with pytest.raises(TypeError):
+        losses.ssim(torch.rand(3, 8, 8), torch.rand(3, 8, 8))
+    with pytest.raises(NotImplementedError):
+        losses.ssim(torch.rand(3, 8, 8), torch.rand(3, 8, 8), window_size=7)
+    # the taps are the reference's (loss_utils.py:112-114): normalised, symmetric, 11 of them
+    assert losses._TAPS11.shape == (11,) and abs(float(losses._TAPS11.sum()) - 1.0) < 1e-6
+    assert np.array_equal(losses._TAPS11, losses._TAPS11[::-1])
+
+
+def _close(got, ref, tol, name, extra=0.0):
+    scale = max(float(np.abs(ref).max()), 1e-12)
+    err = float(np.abs(got - ref).max())
+    assert err <= tol * scale + extra, "%s: max err %.3e vs scale %.3e" % (name, err, scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN)
+def test_gpu_losses_match_reference_golden(golden_dir, name):
+    from gscream_b200 import losses
+    z, img, gt, mask = _load(golden_dir, name)
+    dev = torch.device("cuda")
+    x = img.to(dev).requires_grad_(True)
+    y = gt.to(dev)
+    m = None if mask is None else mask.to(dev)
+    if m is None:
+        s, l = losses.ssim(x, y), losses.l1_loss(x, y)
+    else:
+        s, l = losses.ssim_masked(x, y, m), losses.l1_loss_masked(x, y, m)
+    gs, = torch.autograd.grad(s, x)
+    gl, = torch.autograd.grad(l, x)
+    assert abs(float(s) - float(z["f64.ssim"])) <= 1e-5 * abs(float(z["f64.ssim"]))
+    assert abs(float(l) - float(z["f64.l1"])) <= 1e-5 * abs(float(z["f64.l1"]))
+    _close(gs.cpu().numpy().astype(np.float64), z["f64.g_ssim"], 1e-5, "d ssim / d image", extra=2 * float(np.abs(z["g_ssim"] - z["f64.g_ssim"]).max()))
+    _close(gl.cpu().numpy().astype(np.float64), z["f64.g_l1"], 1e-6, "d l1 / d image")
+    # both terms from one node, arbitrary upstream weights (train.py:539: (1 - lambda) * L1 + lambda * (1 - ssim))
+    x2 = img.to(dev).requires_grad_(True)
+    s2, l2 = losses.l1_ssim(x2, y, m)
+    (0.8 * l2 + 0.2 * (1.0 - s2)).backward()
+    ref = 0.8 * z["f64.g_l1"] - 0.2 * z["f64.g_ssim"]
+    _close(x2.grad.cpu().numpy().astype(np.float64), ref, 1e-5, "combined", extra=2 * float(np.abs(z["g_ssim"] - z["f64.g_ssim"]).max()))
+
+
+@pytest.mark.gpu
+def test_gpu_losses_train_step_size_vs_fp64_restatement():
+    from gscream_b200 import losses
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    C, H, W = 3, 567, 1008
+    img = torch.rand(C, H, W, generator=g)
+    gt = (img + 0.1 * torch.randn(C, H, W, generator=g)).clamp(0, 1)
+    x64 = img.double().to(dev).requires_grad_(True)
+    s64 = ts.ssim(x64, gt.double().to(dev), ts._gaussian_window(device=dev).double())
+    l64 = (x64 - gt.double().to(dev)).abs().mean()
+    g64, = torch.autograd.grad(0.8 * l64 + 0.2 * (1 - s64), x64)
+    x = img.to(dev).requires_grad_(True)
+    s, l = losses.l1_ssim(x, gt.to(dev))
+    (0.8 * l + 0.2 * (1 - s)).backward()
+    assert abs(float(s) - float(s64)) <= 1e-5 * abs(float(s64)) and abs(float(l) - float(l64)) <= 1e-5 * abs(float(l64))
+    _close(x.grad.double().cpu().numpy(), g64.cpu().numpy(), 1e-5, "train-step size gradient")
+    # batched input [B, C, H, W]: planes = B * C
+    xb = torch.stack([img, gt]).to(dev).requires_grad_(True)
+    yb = torch.stack([gt, img]).to(dev)
+    sb, lb = losses.l1_ssim(xb, yb)
+    assert abs(float(sb) - float(s64)) <= 2e-5 * abs(float(s64))   # SSIM and L1 are symmetric in (x, y)
+    assert abs(float(lb) - float(l64)) <= 2e-5 * abs(float(l64))
