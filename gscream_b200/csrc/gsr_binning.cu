@@ -155,9 +155,15 @@ BinningLayout binning_layout(int P, int64_t R, int W, int H)
 // -------- kernels -----------------------------------------------------------------------------
 // Instance emission in depth order (the reference's duplicateWithKeys runs in index order, one thread per Gaussian,
 // and writes 64-bit keys; here the depth is already encoded in the position, so the key is just the tile id).
-// Warp-cooperative: the warp walks its 32 Gaussians one at a time and the lanes write that Gaussian's tile rectangle
-// as consecutive entries — coalesced stores instead of 32 interleaved single-entry streams (one thread per Gaussian
-// was L1-wavefront bound: 616 us at R = 40 M, profiles/r1_sort_ab.md).
+// One lane per INSTANCE: a warp takes 32 consecutive Gaussians of the depth order, whose instances are one contiguous run of
+// the output (offsets is the inclusive scan in that order); lane k of each 32-instance step finds its owner Gaussian by a
+// 5-step binary search over the warp's prefix sums (shuffles), derives the tile from the owner's rectangle and writes
+// (tile id, packed value) to position run_start + k — fully coalesced stores and full lane utilisation whatever the
+// rectangle sizes.  History (profiles/r1_sort_ab.md, r1_feed_ab.md): one thread per Gaussian was L1-wavefront bound
+// (616 us at R = 40 M); one warp iteration per Gaussian left 3/4 of the lanes idle at 7 instances per Gaussian and doubled
+// in cost (77 -> 139 us) once the per-instance warp mask was added.
+// The value carries, above the 24-bit Gaussian id, the 8-bit mask of the tile's warps whose 8x4 pixel block the Gaussian's
+// alpha >= 1/255 bounding box touches (gsr_blend.cuh).
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t *__restrict__ order,
                                                              const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ tiles_touched,
                                                              const float *__restrict__ rec, int gx, int gy, bool packed,
@@ -165,39 +171,50 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 {
 	const int lane = threadIdx.x & 31;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t g = 0, tt = 0, off = 0;
+	uint32_t g = 0, tt = 0, incl = 0;
 	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
 	float2 xy = {0.f, 0.f}, ext = {-1.f, -1.f};
 	if (i < P) {
 		g = order[i];
 		tt = tiles_touched[g];
+		incl = offsets[i]; // inclusive scan of tiles_touched in depth order
 		if (tt != 0) {
-			off = offsets[i] - tt;
 			xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
 			ext = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS + 8);
 			const int radius = (int)rec[(size_t)g * GSR_REC_FLOATS + 13];
 			get_rect(xy.x, xy.y, radius, gx, gy, x0, y0, x1, y1); // same rect as the forward (CR/rasterizer_impl.cu:92)
 		}
 	}
-	uint32_t todo = __ballot_sync(0xffffffffu, tt != 0);
-	while (todo) {
-		const int src = __ffs(todo) - 1;
-		todo &= todo - 1;
+	// the warp's run of the output: [run_start, run_start + total)
+	const uint32_t run_start = __shfl_sync(0xffffffffu, incl - tt, 0);
+	const int last = min(31, P - 1 - (i - lane));                 // last lane of this warp that maps to a Gaussian
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, last < 0 ? 0 : last) - run_start;
+	const uint32_t end_rel = (i < P) ? incl - run_start : total; // exclusive end of this lane's instances within the run
+	const int w = x1 - x0;
+	for (uint32_t kb = 0; kb < total; kb += 32) {
+		const uint32_t k = kb + lane;
+		// owner = first lane whose end_rel > k (lanes without instances have end_rel equal to their predecessor's)
+		int lo = 0;
+#pragma unroll
+		for (int step = 16; step >= 1; step >>= 1) {
+			const uint32_t probe = __shfl_sync(0xffffffffu, end_rel, lo + step - 1);
+			if (probe <= k) lo += step;
+		}
+		const int src = min(lo, 31);
 		const uint32_t s_g = __shfl_sync(0xffffffffu, g, src), s_tt = __shfl_sync(0xffffffffu, tt, src);
-		const uint32_t s_off = __shfl_sync(0xffffffffu, off, src);
-		const int s_x0 = __shfl_sync(0xffffffffu, x0, src), s_y0 = __shfl_sync(0xffffffffu, y0, src);
-		const int w = __shfl_sync(0xffffffffu, x1, src) - s_x0;
+		const uint32_t s_end = __shfl_sync(0xffffffffu, end_rel, src);
+		const int s_x0 = __shfl_sync(0xffffffffu, x0, src), s_y0 = __shfl_sync(0xffffffffu, y0, src), s_w = __shfl_sync(0xffffffffu, w, src);
 		const float s_cx = __shfl_sync(0xffffffffu, xy.x, src), s_cy = __shfl_sync(0xffffffffu, xy.y, src);
 		const float s_hx = __shfl_sync(0xffffffffu, ext.x, src), s_hy = __shfl_sync(0xffffffffu, ext.y, src);
-		// entry e of the rectangle in row-major order (y outer, x inner), as duplicateWithKeys emits it; the value carries
-		// the 8-bit mask of the tile's warps whose pixel block the alpha >= 1/255 bounding box touches (gsr_blend.cuh)
-		for (uint32_t e = lane; e < s_tt; e += 32) {
-			const int ry = (int)e / w, rx = (int)e - ry * w;
+		if (k < total) {
+			// entry e of the rectangle in row-major order (y outer, x inner), as duplicateWithKeys emits it
+			const int e = (int)(k - (s_end - s_tt));
+			const int ry = e / s_w, rx = e - ry * s_w;
 			const int tx = s_x0 + rx, ty = s_y0 + ry;
-			keys[s_off + e] = (uint32_t)(ty * gx + tx);
 			uint32_t v = s_g;
 			if (packed) v |= warp_overlap_mask(s_cx, s_cy, s_hx, s_hy, (float)(tx * GSR_BLOCK_X), (float)(ty * GSR_BLOCK_Y)) << 24;
-			vals[s_off + e] = v;
+			keys[run_start + k] = (uint32_t)(ty * gx + tx);
+			vals[run_start + k] = v;
 		}
 	}
 }
