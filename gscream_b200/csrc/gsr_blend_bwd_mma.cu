@@ -25,6 +25,7 @@
 //          C       cols 2t, 2t+1 of tile nt <-> ch 8t+nt, 8t+4+nt -> two red.global.add.v4.f32 per row
 #include "gsr_blend.cuh"
 #include "gsr_internal.cuh"
+#include "gsr_tf32.cuh"
 
 namespace gsr {
 
@@ -39,26 +40,6 @@ constexpr int kMmaWarpBytes = BlendTraits<kC>::kWarpBytes + kChunk * kTileStride
 #define GSR_BWD_MMA_MINWARPS 16
 #endif
 
-// x = hi + lo with hi a TF32 value.  cvt.rna.tf32.f32 is emulated on sm_100a (IADD, FSETP, SEL, LOP3), so the rounding is done
-// on the bit pattern directly: adding half a TF32 ulp and clearing the low 13 bits rounds to nearest (ties away); Inf
-// becomes NaN, which is where such inputs end up anyway.  lo = x - hi is exact; the tensor core reads its top 19 bits.
-__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo)
-{
-	hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-	lo = __float_as_uint(x - __uint_as_float(hi));
-}
-// truncating variant for operands kept as raw fp32 in registers: hi = x with the low 13 bits cleared (1 op), lo = x - hi
-__device__ __forceinline__ void tf32_split_trunc(float x, uint32_t &hi, uint32_t &lo)
-{
-	hi = __float_as_uint(x) & 0xffffe000u;
-	lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
-{
-	asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-	             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 // gradient block g[p][ch] in shared memory: row p = 32 floats, 16-B units XOR-swizzled by the row
 __device__ __forceinline__ int sg_swz(int p) { return (((p >> 3) & 3) << 1) | (p & 1); }
 __device__ __forceinline__ int sg_index(int p, int ch) { return p * 32 + ((((ch >> 2) ^ sg_swz(p)) << 2) | (ch & 3)); }

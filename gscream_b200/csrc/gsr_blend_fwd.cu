@@ -22,6 +22,7 @@
 // measurements that drove it: DESIGN.md section 4, profiles/r1_staging_ab.md, profiles/r1_feed_ab.md.
 #include "gsr_blend.cuh"
 #include "gsr_internal.cuh"
+#include "gsr_tf32.cuh"
 
 namespace gsr {
 
@@ -130,6 +131,168 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 	}
 }
 
+// ---- C = 32 variant with the colour accumulation on the tensor pipe (-DGSR_FWD_MMA=1) ------------------------------------
+// out[p][ch] += sum_j w[p][j] f[j][ch] over a sub-chunk of 8 staged Gaussians is a [32 x 8] x [8 x 32] product per warp: the scalar
+// kernel spends 32 FFMA + 8 LDS.128 per (pixel lane, contributing Gaussian) on it, 36 % of its instructions, and it is issue
+// bound (90 % issue-slot utilisation, profiles/r1_blend_v5_summary.md).  Here the per-pixel recurrence only produces
+// w = alpha * T (0 for non-contributing pairs) into an 8 x 32 shared tile, and 24 mma.sync.m16n8k8 TF32 (3xTF32 split) per
+// sub-chunk add the product to accumulators held in C-fragment layout:
+//   A = w   rows p = 16 mt + g (+8), k = Gaussian t (+4) of the sub-chunk
+//   B = f   k = Gaussian t (+4), col n = g of tile nt <-> channel 4 g + nt (one LDS.128 per Gaussian covers the four tiles)
+//   C       lane (g, t) holds pixels 16 mt + g (+8), channels 8 t + nt and 8 t + 4 + nt
+#ifndef GSR_FWD_MMA
+#define GSR_FWD_MMA 0
+#endif
+constexpr int kSub = 8;                                   // Gaussians per MMA k-step
+constexpr int kWStride = 40;                              // floats per row of the 8 x 32 weight tile (bank-conflict-free A loads)
+constexpr int kFwdMmaWarpBytes = BlendTraits<32>::kWarpBytes + kSub * kWStride * 4;
+#ifndef GSR_FWD_MMA_MINWARPS
+#define GSR_FWD_MMA_MINWARPS 26
+#endif
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MMA_MINWARPS / kWarpsPerCta) blend_forward_mma_kernel(
+    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
+    const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
+    float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
+    float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_unc)
+{
+	constexpr int C = 32;
+	using TR = BlendTraits<C>;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int tid = threadIdx.x, lwarp = tid >> 5, lane = tid & 31;
+	const int tile = blockIdx.x / kCtasPerTile;
+	const int warp = (blockIdx.x % kCtasPerTile) * kWarpsPerCta + lwarp;
+	const int tile_x0 = (tile % tiles_x) * GSR_BLOCK_X, tile_y0 = (tile / tiles_x) * GSR_BLOCK_Y;
+	int bx, by;
+	warp_block_origin(warp, bx, by);
+	const int px = tile_x0 + bx + (lane & 7), py = tile_y0 + by + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const float pixf_x = (float)px, pixf_y = (float)py;
+	const int fg = lane >> 2, ft = lane & 3;
+
+	const uint2 range = ranges[tile];
+	float T = 1.0f;
+	uint32_t last_contributor = 0, last_ring = 0;
+	float acc[2][4][4]; // [mt][nt][c0..c3]
+#pragma unroll
+	for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+		for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+			for (int i = 0; i < 4; i++) acc[mt][nt][i] = 0.f;
+	float D = 0.f, UNC = 0.f;
+	bool done = !inside;
+
+	if (!__all_sync(0xffffffffu, done)) {
+		unsigned char *wsm = smem_raw + (size_t)lwarp * kFwdMmaWarpBytes;
+		float *s_w = reinterpret_cast<float *>(wsm + TR::kWarpBytes); // [8][40]: alpha * T of the sub-chunk, row = Gaussian, col = pixel
+		WarpFeed<C, false> feed;
+		feed.init(wsm, point_list + range.x, (int)(range.y - range.x), rec, features, warp, lane, packed != 0);
+		feed.fill();
+		int m_cur = feed.issue(0);
+		for (int chunk = 0; m_cur > 0; chunk++) {
+			feed.fill();
+			const int m_next = feed.issue((chunk + 1) & 1);
+			cp_async_wait_but_one();
+			__syncwarp();
+			const float *ent0 = feed.stage + (chunk & 1) * TR::kStageFloats;
+			for (int sub = 0; sub < m_cur; sub += kSub) {
+				const float *ent = ent0 + sub * TR::kEntryFloats;
+				bool any_w = false;
+#pragma unroll
+				for (int e = 0; e < kSub; e++, ent += TR::kEntryFloats) {
+					float w = 0.f;
+					if (sub + e < m_cur) {
+						const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
+						const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
+						const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
+						const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
+						if (!(done || power > 0.0f)) {
+							const float alpha = min(0.99f, __fmul_rn(r1.y, expf(power)));
+							if (!(alpha < kAlphaMin)) {
+								const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
+								if (test_T < 0.0001f) {
+									done = true;
+								} else {
+									w = alpha * T;
+									D += r1.z * w;
+									UNC += r1.w * w;
+									T = test_T;
+									last_ring = feed.done + sub + e + 1u;
+								}
+							}
+						}
+					}
+					s_w[e * kWStride + lane] = w;
+					any_w |= (w != 0.f);
+				}
+				__syncwarp();
+				if (__any_sync(0xffffffffu, any_w)) {
+					// B fragments: Gaussians t and t+4 of the sub-chunk, channels 4g..4g+3 (the four n-tiles)
+					const float *fb = ent0 + (sub + ft) * TR::kEntryFloats + TR::kRecParts * 4 + 4 * fg;
+					const float4 f0 = *reinterpret_cast<const float4 *>(fb), f1 = *reinterpret_cast<const float4 *>(fb + 4 * TR::kEntryFloats);
+					const float b0v[4] = {f0.x, f0.y, f0.z, f0.w}, b1v[4] = {f1.x, f1.y, f1.z, f1.w};
+					uint32_t b0h[4], b0l[4], b1h[4], b1l[4];
+#pragma unroll
+					for (int nt = 0; nt < 4; nt++) {
+						tf32_split(b0v[nt], b0h[nt], b0l[nt]);
+						tf32_split(b1v[nt], b1h[nt], b1l[nt]);
+					}
+#pragma unroll
+					for (int mt = 0; mt < 2; mt++) {
+						uint32_t ah[4], al[4];
+						tf32_split(s_w[ft * kWStride + 16 * mt + fg], ah[0], al[0]);
+						tf32_split(s_w[ft * kWStride + 16 * mt + fg + 8], ah[1], al[1]);
+						tf32_split(s_w[(ft + 4) * kWStride + 16 * mt + fg], ah[2], al[2]);
+						tf32_split(s_w[(ft + 4) * kWStride + 16 * mt + fg + 8], ah[3], al[3]);
+#pragma unroll
+						for (int nt = 0; nt < 4; nt++) {
+							mma_tf32(acc[mt][nt], al[0], al[1], al[2], al[3], b0h[nt], b1h[nt]);
+							mma_tf32(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], b0l[nt], b1l[nt]);
+							mma_tf32(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], b0h[nt], b1h[nt]);
+						}
+					}
+				}
+				__syncwarp(); // the weight tile may be overwritten
+			}
+			if (last_ring > feed.done) last_contributor = feed.q_pos[(last_ring - 1u) & (kRing - 1)] + 1u;
+			feed.done += m_cur;
+			__syncwarp();
+			m_cur = m_next;
+			if (__all_sync(0xffffffffu, done)) break;
+		}
+		cp_async_wait_all();
+	}
+
+	const size_t plane = (size_t)H * W;
+	if (inside) {
+		const size_t pix_id = (size_t)W * py + px;
+		final_T[pix_id] = T;
+		n_contrib[pix_id] = last_contributor;
+		out_depth[pix_id] = D;
+		out_unc[pix_id] = UNC;
+	}
+	// colour planes from the C fragments: pixels p = 16 mt + g (+8) of the warp's 8x4 block, channels 8t + nt and 8t + 4 + nt
+#pragma unroll
+	for (int mt = 0; mt < 2; mt++) {
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			const int p = 16 * mt + fg + 8 * half;
+			const float Tp = __shfl_sync(0xffffffffu, T, p);
+			const int qx = tile_x0 + bx + (p & 7), qy = tile_y0 + by + (p >> 3);
+			if (qx < W && qy < H) {
+				const size_t pix = (size_t)W * qy + qx;
+#pragma unroll
+				for (int nt = 0; nt < 4; nt++) {
+					const int ch0 = 8 * ft + nt, ch1 = ch0 + 4;
+					out_color[ch0 * plane + pix] = acc[mt][nt][2 * half] + Tp * __ldg(bg + ch0);
+					out_color[ch1 * plane + pix] = acc[mt][nt][2 * half + 1] + Tp * __ldg(bg + ch1);
+				}
+			}
+		}
+	}
+}
+
 template <int C>
 static cudaError_t launch_fwd(int tiles, const uint2 *ranges, const uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
                               const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
@@ -156,6 +319,21 @@ cudaError_t launch_blend_forward(int C, int P, int W, int H, const uint2 *ranges
 	const int tiles = tiles_x * tiles_y;
 	if (tiles <= 0) return cudaSuccess;
 	const int packed = point_list_packed(P) ? 1 : 0;
+#if GSR_FWD_MMA
+	if (C == 32) {
+		const size_t smem = (size_t)kWarpsPerCta * kFwdMmaWarpBytes;
+		static bool configured = false;
+		if (!configured) {
+			cudaError_t e = cudaFuncSetAttribute(blend_forward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) return e;
+			configured = true;
+		}
+		blend_forward_mma_kernel<<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg,
+		                                                                                  final_T, n_contrib, out_color, out_depth, out_unc);
+		count_launch();
+		return cudaGetLastError();
+	}
+#endif
 	switch (C) {
 	case 3: return launch_fwd<3>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_T, n_contrib, out_color, out_depth, out_unc, stream);
 	case 32: return launch_fwd<32>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_T, n_contrib, out_color, out_depth, out_unc, stream);
