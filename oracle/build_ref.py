@@ -82,9 +82,20 @@ def build_variant(channels, verbose=False):
 
 
 def build_all(verbose=False):
+    """One subprocess per variant: torch.utils.cpp_extension.load() renames a second module called `_C` built in the same
+    process to `_C_v1` (its JIT version bump), which the staged package would not import."""
+    import subprocess
     for c in (3, 32):
         if not is_built(c):
-            build_variant(c, verbose=verbose)
+            d = variant_dir(c)
+            if os.path.isdir(d):
+                for f in os.listdir(d):
+                    if f.startswith("_C_v") and f.endswith(".so"):
+                        os.remove(os.path.join(d, f))
+            subprocess.run([sys.executable, os.path.abspath(__file__), str(c)], check=True,
+                           stdout=None if verbose else subprocess.DEVNULL, stderr=None if verbose else subprocess.DEVNULL)
+            if not is_built(c):
+                raise RuntimeError("reference build for NUM_CHANNELS=%d did not produce _C.so in %s" % (c, d))
 
 
 if __name__ == "__main__":
