@@ -12,6 +12,8 @@
 namespace gsr {
 
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_plain_point_list{0};
+bool point_list_packed(int P) { return P <= (1 << 24) && !g_plain_point_list.load(std::memory_order_relaxed); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- optional per-stage device timing (bench.py's roofline line) ---------------------------------
@@ -228,6 +230,11 @@ int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const
 	a.accumulate = accumulate;
 	{ StageTimer t(kPreBwd, stream); GSR_CUDA(launch_preprocess_backward(a, stream)); }
 	return 0;
+}
+
+int gsr_debug_plain_point_list(int on)
+{
+	return g_plain_point_list.exchange(on ? 1 : 0);
 }
 
 int gsr_profile_enable(int on)

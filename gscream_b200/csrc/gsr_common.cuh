@@ -99,7 +99,8 @@ __device__ __forceinline__ uint32_t warp_overlap_mask(float cx, float cy, float 
 
 // point_list entries carry that mask in their top byte when every Gaussian id fits 24 bits (P <= 2^24); above that the
 // entries are plain ids and the blend kernels treat every instance as a candidate for every warp (still exact, slower).
-__host__ __device__ inline bool point_list_packed(int P) { return P <= (1 << 24); }
+// (Host-side decision; gsr_debug_plain_point_list(1) forces the plain form so that tests can cover it at small P.)
+bool point_list_packed(int P);
 
 // mbarrier + bulk-async (TMA, non-tensor form: SASS UBLKCP) wrappers, sm_90+/sm_100a.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

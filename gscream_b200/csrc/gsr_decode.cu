@@ -34,9 +34,12 @@ __host__ __device__ inline int out_count(int m, int k) { return m == 0 ? k : m =
 __device__ __forceinline__ int mlp_of(int o, int k) { return o < k ? 0 : (o < 2 * k ? 1 : (o < 9 * k ? 2 : 3)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// shared-memory carve-up (in floats)
+// shared-memory carve-up (in floats).  One padded copy of each weight matrix serves both access patterns:
+//   W1 as [m][i][33]  : forward layer 1 reads a row with lane = h (consecutive), backward layer 1 a column with lane = i (stride 33)
+//   W2 as [h][Os], Os odd >= 12k : forward layer 2 reads with lane = o (consecutive), backward layer 2 with lane = h (stride Os)
+constexpr int kW1Stride = kHid + 1;
 struct SmemPlan {
-	int w1t, w1, b1, w2t, w2, b2, warp0, per_warp, x4, h4, dh4, out4, pp, total;
+	int w1, b1, w2, os, b2, warp0, per_warp, x4, h4, dh4, out4, pp, total;
 };
 __host__ __device__ inline SmemPlan smem_plan(int k, bool backward)
 {
@@ -44,19 +47,19 @@ __host__ __device__ inline SmemPlan smem_plan(int k, bool backward)
 	const int Opad = (O + 3) & ~3;
 	SmemPlan p{};
 	int off = 0;
-	p.w1t = off; off += 4 * kIn * kHid;                 // [m][i][h]   (forward layer 1: lane = h)
-	p.w1 = off;  if (backward) off += 4 * kHid * kIn;   // [m][h][i]   (backward layer 1: lane = i)
+	p.w1 = off;  off += 4 * kIn * kW1Stride;
 	p.b1 = off;  off += 4 * kHid;
-	p.w2t = off; off += kHid * Opad;                    // [h][o]      (forward layer 2: lane = o)
-	p.w2 = off;  if (backward) off += Opad * kHid;      // [o][h]      (backward layer 2: lane = h)
+	p.os = O | 1;
+	p.w2 = off;  off += kHid * p.os;
 	p.b2 = off;  off += Opad;
+	off = (off + 3) & ~3;
 	p.warp0 = off;
 	int w = 0;
 	p.x4 = w;   w += kIn * kNA;                         // [i][a]
 	p.h4 = w;   w += 4 * kHStride * kNA;                // [m][h(+1)][a]
 	p.dh4 = w;  if (backward) w += 4 * kHStride * kNA;
 	p.out4 = w; w += Opad * kNA;                        // [o][a]  (pre-activations, then their gradients in place)
-	p.pp = w;   if (backward) w += kNA * kDecMaxK * 12; // per (anchor, offset) partials: dxyz(3) dgs(6)
+	p.pp = w;   if (backward) w += ((kNA * k * 10 + 3) & ~3); // per (anchor, offset) partials: dxyz(3) dgs(6)
 	p.per_warp = w;
 	p.total = off + kWarps * w;
 	return p;
@@ -70,22 +73,18 @@ struct GroupIO {
 	float dist[kNA];
 };
 
-__device__ __forceinline__ void load_weights(float *sm, const SmemPlan &pl, const DecodeWeights &wt, int k, bool backward, int tid)
+__device__ __forceinline__ void load_weights(float *sm, const SmemPlan &pl, const DecodeWeights &wt, int k, int tid)
 {
-	const int O = 12 * k, Opad = (O + 3) & ~3;
+	const int O = 12 * k;
 	for (int idx = tid; idx < 4 * kHid * kIn; idx += 256) {
 		const int m = idx / (kHid * kIn), rem = idx % (kHid * kIn), h = rem / kIn, i = rem % kIn;
-		const float v = __ldg(wt.w1[m] + rem);
-		sm[pl.w1t + (m * kIn + i) * kHid + h] = v;
-		if (backward) sm[pl.w1 + idx] = v;
+		sm[pl.w1 + (m * kIn + i) * kW1Stride + h] = __ldg(wt.w1[m] + rem);
 	}
 	for (int idx = tid; idx < 4 * kHid; idx += 256) sm[pl.b1 + idx] = __ldg(wt.b1[idx >> 5] + (idx & 31));
 	for (int idx = tid; idx < O * kHid; idx += 256) {
 		const int o = idx / kHid, h = idx % kHid;
 		const int m = o < k ? 0 : (o < 2 * k ? 1 : (o < 9 * k ? 2 : 3));
-		const float v = __ldg(wt.w2[m] + (o - out_base(m, k)) * kHid + h);
-		sm[pl.w2t + h * Opad + o] = v;
-		if (backward) sm[pl.w2 + o * kHid + h] = v;
+		sm[pl.w2 + h * pl.os + o] = __ldg(wt.w2[m] + (o - out_base(m, k)) * kHid + h);
 	}
 	for (int o = tid; o < O; o += 256) {
 		const int m = o < k ? 0 : (o < 2 * k ? 1 : (o < 9 * k ? 2 : 3));
@@ -93,32 +92,52 @@ __device__ __forceinline__ void load_weights(float *sm, const SmemPlan &pl, cons
 	}
 }
 
-// Gather one group of kNA visible anchors and build X4[i][a] = [feat | ob_view | ob_dist]
-// (gaussian_renderer/__init__.py:26-52).  Anchors past n_vis contribute zeros.
-__device__ __forceinline__ void load_group(GroupIO &io, float *X4, int g, int n_vis, const uint32_t *__restrict__ vis_ids,
-                                           const float *__restrict__ anchor, const float *__restrict__ feat, float cx, float cy, float cz, int lane)
+// One group of kNA visible anchors as it comes from global memory.  Fetched one loop iteration ahead of its use, so that the
+// two dependent loads (visible list -> anchor row / feature row) are off the critical path of the MLP arithmetic.
+struct GroupRaw {
+	int id[kNA];
+	bool valid[kNA];
+	float f[kNA];                      // feature `lane` of each anchor
+	float ax[kNA], ay[kNA], az[kNA];
+};
+__device__ __forceinline__ void fetch_group(GroupRaw &r, int g, int groups, int n_vis, const uint32_t *__restrict__ vis_ids,
+                                            const float *__restrict__ anchor, const float *__restrict__ feat, int lane)
 {
 #pragma unroll
 	for (int a = 0; a < kNA; a++) {
-		const int r = g * kNA + a;
-		io.valid[a] = r < n_vis;
-		io.id[a] = io.valid[a] ? (vis_ids ? (int)__ldg(vis_ids + r) : r) : 0;
-		float f = 0.f;
-		io.ax[a] = io.ay[a] = io.az[a] = 0.f;
+		const int rank = g * kNA + a;
+		r.valid[a] = g < groups && rank < n_vis;
+		r.id[a] = r.valid[a] ? (vis_ids ? (int)__ldg(vis_ids + rank) : rank) : 0;
+	}
+#pragma unroll
+	for (int a = 0; a < kNA; a++) {
+		r.f[a] = r.ax[a] = r.ay[a] = r.az[a] = 0.f;
+		if (r.valid[a]) {
+			r.f[a] = __ldg(feat + (size_t)r.id[a] * kHid + lane);
+			r.ax[a] = __ldg(anchor + (size_t)r.id[a] * 3 + 0);
+			r.ay[a] = __ldg(anchor + (size_t)r.id[a] * 3 + 1);
+			r.az[a] = __ldg(anchor + (size_t)r.id[a] * 3 + 2);
+		}
+	}
+}
+// Build X4[i][a] = [feat | ob_view | ob_dist] (gaussian_renderer/__init__.py:26-52).  Anchors past n_vis contribute zeros.
+__device__ __forceinline__ void stage_group(GroupIO &io, float *X4, const GroupRaw &r, float cx, float cy, float cz, int lane)
+{
+#pragma unroll
+	for (int a = 0; a < kNA; a++) {
+		io.valid[a] = r.valid[a];
+		io.id[a] = r.id[a];
+		io.ax[a] = r.ax[a]; io.ay[a] = r.ay[a]; io.az[a] = r.az[a];
 		io.ux[a] = io.uy[a] = io.uz[a] = 0.f;
 		io.dist[a] = 0.f;
 		if (io.valid[a]) {
-			f = __ldg(feat + (size_t)io.id[a] * kHid + lane);
-			io.ax[a] = __ldg(anchor + (size_t)io.id[a] * 3 + 0);
-			io.ay[a] = __ldg(anchor + (size_t)io.id[a] * 3 + 1);
-			io.az[a] = __ldg(anchor + (size_t)io.id[a] * 3 + 2);
 			const float vx = io.ax[a] - cx, vy = io.ay[a] - cy, vz = io.az[a] - cz;
 			io.dist[a] = sqrtf(vx * vx + vy * vy + vz * vz);
 			io.ux[a] = vx / io.dist[a];
 			io.uy[a] = vy / io.dist[a];
 			io.uz[a] = vz / io.dist[a];
 		}
-		X4[lane * kNA + a] = f;
+		X4[lane * kNA + a] = r.f[a];
 		if (lane < 4) X4[(kHid + lane) * kNA + a] = lane == 0 ? io.ux[a] : lane == 1 ? io.uy[a] : lane == 2 ? io.uz[a] : io.dist[a];
 	}
 	__syncwarp();
@@ -140,7 +159,7 @@ __device__ __forceinline__ void layer1(const float *sm, const SmemPlan &pl, cons
 		const float4 x = *reinterpret_cast<const float4 *>(X4 + i * kNA);
 #pragma unroll
 		for (int m = M0; m < M1; m++) {
-			const float w = sm[pl.w1t + (m * kIn + i) * kHid + lane];
+			const float w = sm[pl.w1 + (m * kIn + i) * kW1Stride + lane];
 			acc[m - M0][0] = fmaf(w, x.x, acc[m - M0][0]);
 			acc[m - M0][1] = fmaf(w, x.y, acc[m - M0][1]);
 			acc[m - M0][2] = fmaf(w, x.z, acc[m - M0][2]);
@@ -158,7 +177,6 @@ __device__ __forceinline__ void layer1(const float *sm, const SmemPlan &pl, cons
 // Layer 2 for outputs [o_begin, o_end): lane = output unit.  OUT4[o][a] = b2[o] + sum_h W2[o][h] H[m(o)][h][a].
 __device__ __forceinline__ void layer2(const float *sm, const SmemPlan &pl, const float *H4, float *OUT4, int k, int o_begin, int o_end, int lane)
 {
-	const int Opad = (12 * k + 3) & ~3;
 	for (int o0 = o_begin; o0 < o_end; o0 += 32) {
 		const int o = o0 + lane;
 		const bool on = o < o_end;
@@ -169,7 +187,7 @@ __device__ __forceinline__ void layer2(const float *sm, const SmemPlan &pl, cons
 		const float *hrow = H4 + m * kHStride * kNA;
 #pragma unroll 8
 		for (int h = 0; h < kHid; h++) {
-			const float w = sm[pl.w2t + h * Opad + oc];
+			const float w = sm[pl.w2 + h * pl.os + oc];
 			const float4 hv = *reinterpret_cast<const float4 *>(hrow + h * kNA);
 			acc0 = fmaf(w, hv.x, acc0);
 			acc1 = fmaf(w, hv.y, acc1);
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(256) decode_opacity_kernel(DecodeArgs a)
 	const int k = a.k;
 	const SmemPlan pl = smem_plan(k, false);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	load_weights(sm, pl, a.wt, k, false, tid);
+	load_weights(sm, pl, a.wt, k, tid);
 	__syncthreads();
 	float *X4 = sm + pl.warp0 + warp * pl.per_warp + pl.x4;
 	float *H4 = sm + pl.warp0 + warp * pl.per_warp + pl.h4;
@@ -196,9 +214,12 @@ __global__ void __launch_bounds__(256) decode_opacity_kernel(DecodeArgs a)
 	const int n_vis = a.n_vis_dev ? (int)*a.n_vis_dev : a.n_vis;
 	const int groups = (n_vis + kNA - 1) / kNA;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
+	GroupRaw raw;
+	fetch_group(raw, blockIdx.x * kWarps + warp, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
 	for (int g = blockIdx.x * kWarps + warp; g < groups; g += gridDim.x * kWarps) {
 		GroupIO io;
-		load_group(io, X4, g, n_vis, a.vis_ids, a.anchor, a.feat, cx, cy, cz, lane);
+		stage_group(io, X4, raw, cx, cy, cz, lane);
+		fetch_group(raw, g + gridDim.x * kWarps, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
 		layer1<0, 1>(sm, pl, X4, H4, lane);
 		layer2(sm, pl, H4, OUT4, k, 0, k, lane);
 		// lanes = (anchor, offset) pairs; k <= 16 so 4 anchors need at most two rounds
@@ -236,7 +257,7 @@ __global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a)
 	const int k = a.k;
 	const SmemPlan pl = smem_plan(k, false);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	load_weights(sm, pl, a.wt, k, false, tid);
+	load_weights(sm, pl, a.wt, k, tid);
 	__syncthreads();
 	float *X4 = sm + pl.warp0 + warp * pl.per_warp + pl.x4;
 	float *H4 = sm + pl.warp0 + warp * pl.per_warp + pl.h4;
@@ -244,9 +265,12 @@ __global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a)
 	const int n_vis = a.n_vis;
 	const int groups = (n_vis + kNA - 1) / kNA;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
+	GroupRaw raw;
+	fetch_group(raw, blockIdx.x * kWarps + warp, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
 	for (int g = blockIdx.x * kWarps + warp; g < groups; g += gridDim.x * kWarps) {
 		GroupIO io;
-		load_group(io, X4, g, n_vis, a.vis_ids, a.anchor, a.feat, cx, cy, cz, lane);
+		stage_group(io, X4, raw, cx, cy, cz, lane);
+		fetch_group(raw, g + gridDim.x * kWarps, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
 		layer1<1, 4>(sm, pl, X4, H4, lane);
 		layer2(sm, pl, H4, OUT4, k, k, 12 * k, lane);
 		for (int idx = lane; idx < kNA * k; idx += 32) {
@@ -287,13 +311,13 @@ __global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a)
 // every thread adds its slice of the weight-gradient outer products into registers; one atomic per entry at the end.
 constexpr int kAcc2 = (7 * kDecMaxK + 3) / 4;   // output rows of W2 owned by one thread (cov MLP over 4 warps)
 
-__global__ void __launch_bounds__(256) decode_backward_kernel(DecodeBwdArgs a)
+__global__ void __launch_bounds__(256, 2) decode_backward_kernel(DecodeBwdArgs a)
 {
 	extern __shared__ __align__(16) float sm[];
 	const int k = a.f.k, O = 12 * k;
 	const SmemPlan pl = smem_plan(k, true);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	load_weights(sm, pl, a.f.wt, k, true, tid);
+	load_weights(sm, pl, a.f.wt, k, tid);
 	__syncthreads();
 	float *X4 = sm + pl.warp0 + warp * pl.per_warp + pl.x4;
 	float *H4 = sm + pl.warp0 + warp * pl.per_warp + pl.h4;
@@ -323,10 +347,13 @@ __global__ void __launch_bounds__(256) decode_backward_kernel(DecodeBwdArgs a)
 	for (int q = 0; q < kAcc2; q++) acc2[q] = 0.f;
 	float accb2 = 0.f;
 
+	GroupRaw raw;
+	fetch_group(raw, blockIdx.x * kWarps + warp, groups, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, lane);
 	for (int it = 0; it < cta_iters; it++) {
 		const int g = (it * gridDim.x + blockIdx.x) * kWarps + warp;
 		GroupIO io;
-		load_group(io, X4, g < groups ? g : groups, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, cx, cy, cz, lane); // g >= groups: all invalid
+		stage_group(io, X4, raw, cx, cy, cz, lane); // g >= groups: all invalid
+		fetch_group(raw, g + gridDim.x * kWarps, groups, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, lane);
 		layer1<0, 4>(sm, pl, X4, H4, lane);
 		layer2(sm, pl, H4, OUT4, k, 0, O, lane);
 
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(256) decode_backward_kernel(DecodeBwdArgs a)
 #pragma unroll
 				for (int c = 0; c < 3; c++) OUT4[(9 * k + 3 * j + c) * kNA + aa] = d_col[c];
 #pragma unroll
-				for (int c = 0; c < 9; c++) PP[(aa * kDecMaxK + j) * 12 + c] = pp[c];
+				for (int c = 0; c < 9; c++) PP[(aa * k + j) * 10 + c] = pp[c];
 			}
 		}
 		__syncwarp();
@@ -422,7 +449,7 @@ __global__ void __launch_bounds__(256) decode_backward_kernel(DecodeBwdArgs a)
 			float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 			const int ob = out_base(m, k), oe = ob + out_count(m, k);
 			for (int o = ob; o < oe; o++) {
-				const float w = sm[pl.w2 + o * kHid + lane];
+				const float w = sm[pl.w2 + lane * pl.os + o];
 				const float4 dv = *reinterpret_cast<const float4 *>(OUT4 + o * kNA);
 				d0 = fmaf(w, dv.x, d0);
 				d1 = fmaf(w, dv.y, d1);
@@ -441,8 +468,8 @@ __global__ void __launch_bounds__(256) decode_backward_kernel(DecodeBwdArgs a)
 			const int ie = kHid + (lane & 3);
 			for (int mh = 0; mh < 4 * kHid; mh++) {
 				const int m = mh >> 5, h = mh & 31;
-				const float w = sm[pl.w1 + mh * kIn + lane];
-				const float we = sm[pl.w1 + mh * kIn + ie];
+				const float w = sm[pl.w1 + (m * kIn + lane) * kW1Stride + h];
+				const float we = sm[pl.w1 + (m * kIn + ie) * kW1Stride + h];
 				const float4 dv = *reinterpret_cast<const float4 *>(DH4 + (m * kHStride + h) * kNA);
 				dx[0] = fmaf(w, dv.x, dx[0]); dx[1] = fmaf(w, dv.y, dx[1]); dx[2] = fmaf(w, dv.z, dx[2]); dx[3] = fmaf(w, dv.w, dx[3]);
 				de[0] = fmaf(we, dv.x, de[0]); de[1] = fmaf(we, dv.y, de[1]); de[2] = fmaf(we, dv.z, de[2]); de[3] = fmaf(we, dv.w, de[3]);
@@ -457,7 +484,7 @@ __global__ void __launch_bounds__(256) decode_backward_kernel(DecodeBwdArgs a)
 				if (lane < 9) {
 					// sum this anchor's per-offset partials: [0..2] d anchor (from xyz), [3..8] d get_scaling
 					float s = 0.f;
-					for (int j = 0; j < k; j++) s += PP[(aa * kDecMaxK + j) * 12 + lane];
+					for (int j = 0; j < k; j++) s += PP[(aa * k + j) * 10 + lane];
 					if (lane < 3) {
 						const float u = lane == 0 ? io.ux[aa] : lane == 1 ? io.uy[aa] : io.uz[aa];
 						const float gu = lane == 0 ? gux : lane == 1 ? guy : guz;
@@ -610,8 +637,8 @@ cudaError_t decode_backward(const DecodeBwdArgs &a, cudaStream_t stream)
 	cudaError_t e;
 	const size_t smem = (size_t)smem_plan(a.f.k, true).total * 4;
 	if ((e = set_smem(decode_backward_kernel, smem)) != cudaSuccess) return e;
-	// 1 CTA/SM (147 KB of shared memory at k = 10), persistent
-	decode_backward_kernel<<<grid_for(a.f.n_vis, 1), 256, smem, stream>>>(a);
+	// persistent; 2 CTAs/SM (102 KB of shared memory each at k = 10, 128 registers)
+	decode_backward_kernel<<<grid_for(a.f.n_vis, 2), 256, smem, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }

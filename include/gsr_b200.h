@@ -222,6 +222,12 @@ GSR_API int gsr_debug_export(
     uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib,
     gsr_stream_t stream);
 
+/* Test hook: the sorted instance list normally carries an 8-bit per-warp overlap mask above a 24-bit Gaussian id; for more than
+ * 2^24 Gaussians it falls back to plain ids (every warp then treats every instance as a candidate: same results, slower).
+ * gsr_debug_plain_point_list(1) forces that fallback at any size so that it can be tested; returns the previous setting.
+ * Must not be toggled between a forward and its backward. */
+GSR_API int gsr_debug_plain_point_list(int on);
+
 /*
  * Optional per-stage device timing for benchmarks.  gsr_profile_enable(1) (re)starts recording: every stage
  * launch is bracketed by a cudaEvent pair on the caller's stream (up to 256 per stage, nothing is

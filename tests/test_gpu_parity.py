@@ -359,6 +359,31 @@ def test_three_digit_passes_of_the_tile_sort():
     _compare_with_reference_build(sc, cam, grads, C)
 
 
+@pytest.mark.parametrize("name", ["c32_small", "c3_ragged"])
+def test_plain_point_list_fallback_matches_golden(name):
+    """More than 2^24 Gaussians do not fit the 24-bit id + 8-bit warp mask packing of point_list; the library then emits plain
+    ids and every warp treats every instance as a candidate.  Forced here at small P through the test hook: same bit-exact
+    lists / n_contrib / final_T and the same planes and gradients as the packed path."""
+    _require_native()
+    from gscream_b200 import _lib
+    lib = _lib.load()
+    g = load_golden(name)
+    scene, cam, grads = _scene_from_golden(g)
+    P, W, H = int(g["P"]), cam["W"], cam["H"]
+    prev = lib.gsr_debug_plain_point_list(1)
+    try:
+        m = ru.run_impl(ours, scene, cam, grads)
+        e = _export(m, P, W, H)
+    finally:
+        lib.gsr_debug_plain_point_list(prev)
+    geom = dict(tiles_touched=g["geom_tiles_touched"], means2D=g["geom_means2D"], depths=g["geom_depths"], conic_opacity=g["geom_conic_opacity"])
+    img = dict(ranges=g["img_ranges"], n_contrib=g["img_n_contrib"], final_T=g["img_final_T"])
+    _check_ints_and_projection(m, e, g["radii"], geom, img, g["bin_point_list"], int(g["num_rendered"]))
+    ref = {k: g[k] for k in ["color", "depth", "uncertainty", "radii"] + GRAD_KEYS}
+    spread = {k: float(np.abs(g["rerun_" + k] - g[k]).max()) for k in GRAD_KEYS}
+    _check_floats(m, ref, spread)
+
+
 # ---- (4) size-independent properties at full size --------------------------------------------------------------
 def test_properties_at_full_size():
     _require_native()
