@@ -167,7 +167,7 @@ int gsr_forward_stage2(int P, int C, int64_t num_rendered, const float *colors_p
 	{ StageTimer t(kBin, stream); GSR_CUDA(bin_instances(P, num_rendered, width, height, geom, GL, binning, BL, image, IL, stream)); }
 	{
 		StageTimer t(kBlendFwd, stream);
-		GSR_CUDA(launch_blend_forward(C, P, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
+		GSR_CUDA(launch_blend_forward(C, P, width, height, (const uint2 *)(image + IL.ranges), (uint32_t *)(binning + BL.val[point_list_index(width, height)]),
 		                              (const float *)(geom + GL.rec), colors_precomp, background, (float *)(image + IL.final_T),
 		                              (uint32_t *)(image + IL.n_contrib), out_color, out_depth, out_uncertainty, stream));
 	}

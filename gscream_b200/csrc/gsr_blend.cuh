@@ -75,7 +75,8 @@ struct WarpFeed {
 	bool packed;
 
 	__device__ __forceinline__ int pos_of(int ordinal) const { return kReverse ? n - 1 - ordinal : ordinal; }
-	__device__ __forceinline__ uint32_t load_entry(int ordinal) const { return ordinal < n ? __ldg(list + pos_of(ordinal)) : 0u; }
+	// plain (not read-only-path) load: the forward kernel clears mask bits of this list while it runs (see blend_forward_kernel)
+	__device__ __forceinline__ uint32_t load_entry(int ordinal) const { return ordinal < n ? list[pos_of(ordinal)] : 0u; }
 
 	__device__ __forceinline__ void init(unsigned char *warp_smem, const uint32_t *list_, int n_, const float *rec_, const float *feat_,
 	                                     int warp_, int lane_, bool packed_)

@@ -36,7 +36,7 @@ constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 #endif
 template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPerTile) blend_forward_kernel(
-    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
+    const uint2 *__restrict__ ranges, uint32_t *point_list, int packed, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
     float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_unc)
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 			cp_async_wait_but_one();
 			__syncwarp(); // every lane's copies of this chunk have landed
 			const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
+			uint32_t blended = 0; // bit e: this pixel blended entry e of the chunk
 			for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats) {
 				const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
 				const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
@@ -109,6 +110,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 				UNC += r1.w * w;
 				T = test_T;
 				last_ring = feed.done + e + 1u;
+				blended |= 1u << e;
+			}
+			// Instances this warp examined but none of its 32 pixels blended: clear the warp's bit in the instance's mask, so that
+			// the backward pass (which scans the same list with the same masks) visits exactly the contributing (warp, instance) pairs
+			// — 30 % fewer than the bounding-box candidates.  Only this warp tests this bit, and only before clearing it.
+			if (packed) {
+				const uint32_t any_blended = __reduce_or_sync(0xffffffffu, blended);
+				if (lane < m_cur && !((any_blended >> lane) & 1u))
+					atomicAnd(point_list + range.x + feed.q_pos[(feed.done + lane) & (kRing - 1)], ~(1u << (24 + warp)));
 			}
 			if (last_ring > feed.done) last_contributor = feed.q_pos[(last_ring - 1u) & (kRing - 1)] + 1u; // resolve before the ring moves on
 			feed.done += m_cur;
@@ -151,7 +161,7 @@ constexpr int kFwdMmaWarpBytes = BlendTraits<32>::kWarpBytes + kSub * kWStride *
 #endif
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MMA_MINWARPS / kWarpsPerCta) blend_forward_mma_kernel(
-    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
+    const uint2 *__restrict__ ranges, uint32_t *point_list, int packed, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
     float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_unc)
@@ -196,6 +206,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MMA_MINWARPS / kWar
 			cp_async_wait_but_one();
 			__syncwarp();
 			const float *ent0 = feed.stage + (chunk & 1) * TR::kStageFloats;
+			uint32_t blended = 0;
 			for (int sub = 0; sub < m_cur; sub += kSub) {
 				const float *ent = ent0 + sub * TR::kEntryFloats;
 				bool any_w = false;
@@ -219,6 +230,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MMA_MINWARPS / kWar
 									UNC += r1.w * w;
 									T = test_T;
 									last_ring = feed.done + sub + e + 1u;
+									blended |= 1u << (sub + e);
 								}
 							}
 						}
@@ -254,6 +266,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MMA_MINWARPS / kWar
 					}
 				}
 				__syncwarp(); // the weight tile may be overwritten
+			}
+			if (packed) {
+				const uint32_t any_blended = __reduce_or_sync(0xffffffffu, blended);
+				if (lane < m_cur && !((any_blended >> lane) & 1u))
+					atomicAnd(point_list + range.x + feed.q_pos[(feed.done + lane) & (kRing - 1)], ~(1u << (24 + warp)));
 			}
 			if (last_ring > feed.done) last_contributor = feed.q_pos[(last_ring - 1u) & (kRing - 1)] + 1u;
 			feed.done += m_cur;
@@ -294,7 +311,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MMA_MINWARPS / kWar
 }
 
 template <int C>
-static cudaError_t launch_fwd(int tiles, const uint2 *ranges, const uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
+static cudaError_t launch_fwd(int tiles, const uint2 *ranges, uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
                               const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
                               float *out_depth, float *out_unc, cudaStream_t stream)
 {
@@ -311,7 +328,7 @@ static cudaError_t launch_fwd(int tiles, const uint2 *ranges, const uint32_t *po
 	return cudaGetLastError();
 }
 
-cudaError_t launch_blend_forward(int C, int P, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+cudaError_t launch_blend_forward(int C, int P, int W, int H, const uint2 *ranges, uint32_t *point_list, const float *rec,
                                  const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
                                  float *out_depth, float *out_unc, cudaStream_t stream)
 {

@@ -47,7 +47,7 @@ cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const Geom
                           char *image, const ImageLayout &IL, cudaStream_t stream);
 int depth_order_index();
 int point_list_index(int W, int H);
-cudaError_t launch_blend_forward(int C, int P, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+cudaError_t launch_blend_forward(int C, int P, int W, int H, const uint2 *ranges, uint32_t *point_list, const float *rec,
                                  const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
                                  float *out_depth, float *out_unc, cudaStream_t stream);
 cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
