@@ -421,10 +421,11 @@ def run_train_step(args, rank, world, local):
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic anchors / target image / target depth (the SPIN-NeRF 'book' scene and train.py's dependencies are absent)",
            "config": {"workload": "config4 substitute: %d anchors x %d offsets, %dx%d, prefilter + decode + rasterize (RGB+depth+uncertainty) + "
-                                  "L1/SSIM/aligned-depth losses + Adam; P = %d Gaussians from %d visible anchors" % (A, k, W, H, loop.last["P"], loop.last["n_vis"]),
+                                  "L1/SSIM/aligned-depth losses + densification statistics + Adam; P = %d Gaussians from %d visible anchors" % (A, k, W, H, loop.last["P"], loop.last["n_vis"]),
                       "decode": "fused CUDA (gsr_decode_*)" if args.impl == "ours" else "torch eager (reference code path)",
                       "rasterizer": "libgsr_b200" if args.impl == "ours" else "reference CUDA build (oracle/_ref/dgr3)",
-                      "losses": "fused L1 + SSIM (gsr_l1_ssim_*), eager aligned-depth loss and Adam" if args.impl == "ours" else "torch eager"},
+                      "losses": "fused L1 + SSIM (gsr_l1_ssim_*), eager aligned-depth loss and Adam" if args.impl == "ours" else "torch eager",
+                      "densification_statistics": "fused (gsr_training_statis)" if args.impl == "ours" else "torch eager (reference method)"},
            "clocks": clocks}
     if args.impl == "reference":
         out["impl"] = "reference"

@@ -35,6 +35,8 @@ PROTOTYPES = {
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_decode_backward": (_i, [_i, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsr_training_statis_scratch_bytes": (_sz, [_i, _i]),
+    "gsr_training_statis": (_i, [_i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsr_l1_ssim_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gsr_l1_ssim_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "gsr_debug_plain_point_list": (_i, [_i]),

@@ -403,6 +403,26 @@ int gsr_decode_backward(int A, int feat_dim, int n_offsets, int64_t n_vis, int64
 	return 0;
 }
 
+// ---- densification statistics ------------------------------------------------------------------------------------------------
+size_t gsr_training_statis_scratch_bytes(int A, int n_offsets) { return statis_scratch_bytes(A, n_offsets); }
+
+int gsr_training_statis(int A, int n_offsets, int64_t n_vis, int64_t P, const uint8_t *anchor_visible_mask, const uint8_t *offset_selection_mask,
+                        const uint8_t *update_filter, const float *neural_opacity, const float *viewspace_grad, float *opacity_accum,
+                        float *anchor_demon, float *offset_gradient_accum, float *offset_denom, void *scratch, size_t scratch_bytes,
+                        gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (A < 0 || n_offsets < 1 || n_vis < 0 || n_vis > A || P < 0 || P > n_vis * n_offsets) return GSR_E_BADARG;
+	if (A == 0 || n_vis == 0) return 0;
+	if (!anchor_visible_mask || !offset_selection_mask || !neural_opacity || !opacity_accum || !anchor_demon || !offset_gradient_accum || !offset_denom || !scratch)
+		return GSR_E_BADARG;
+	if (P > 0 && (!update_filter || !viewspace_grad)) return GSR_E_BADARG;
+	if (scratch_bytes < statis_scratch_bytes(A, n_offsets) || !aligned16(scratch)) return GSR_E_WORKSPACE;
+	GSR_CUDA(training_statis(A, n_offsets, n_vis, anchor_visible_mask, offset_selection_mask, update_filter, neural_opacity, viewspace_grad,
+	                         opacity_accum, anchor_demon, offset_gradient_accum, offset_denom, (char *)scratch, stream));
+	return 0;
+}
+
 // ---- fused L1 + SSIM image loss -------------------------------------------------------------------------------------------
 int gsr_l1_ssim_forward(int planes, int height, int width, const float *taps11_host, const float *image, const float *target,
                         const float *mask, int mask_planes, double *sums, float *partials, gsr_stream_t stream_)

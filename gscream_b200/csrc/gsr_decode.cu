@@ -535,6 +535,40 @@ __global__ void __launch_bounds__(256, 2) decode_backward_kernel(DecodeBwdArgs a
 	if (lane < o_cnt) atomicAdd(a.g_b2[m2] + (o_first + lane - out_base(m2, k)), accb2);
 }
 
+// ---- densification statistics (scene/gaussian_model.py:729-757, GaussianModel.training_statis) --------------------------------
+// One thread per anchor.  vis_incl / sel_incl are inclusive scans of the anchor-visibility mask and of the offset selection
+// mask (neural_opacity > 0) — the same bookkeeping the reference does with boolean-mask assignments:
+//   opacity_accum[a]            += sum_j max(neural_opacity[r, j], 0)           for visible anchors (r = visible rank)
+//   anchor_demon[a]             += 1
+//   offset_gradient_accum[a, j] += |viewspace_grad[p, :2]|,  offset_denom[a, j] += 1   for selected offsets whose Gaussian p has radii > 0
+__global__ void __launch_bounds__(256) training_statis_kernel(int A, int k, const uint8_t *__restrict__ anchor_visible, const uint32_t *__restrict__ vis_incl,
+                                                              const uint8_t *__restrict__ offset_selected, const uint32_t *__restrict__ sel_incl,
+                                                              const uint8_t *__restrict__ update_filter, const float *__restrict__ neural_opacity,
+                                                              const float *__restrict__ viewspace_grad, float *__restrict__ opacity_accum,
+                                                              float *__restrict__ anchor_demon, float *__restrict__ offset_gradient_accum,
+                                                              float *__restrict__ offset_denom)
+{
+	const int a = blockIdx.x * blockDim.x + threadIdx.x;
+	if (a >= A || !anchor_visible[a]) return;
+	const size_t r = (size_t)vis_incl[a] - 1;
+	float osum = 0.f;
+	for (int j = 0; j < k; j++) {
+		const size_t t = r * k + j;
+		const float o = neural_opacity[t];
+		osum += o < 0.f ? 0.f : o;
+		if (offset_selected[t]) {
+			const size_t p = (size_t)sel_incl[t] - 1;
+			if (update_filter[p]) {
+				const float gx = viewspace_grad[p * 3 + 0], gy = viewspace_grad[p * 3 + 1];
+				offset_gradient_accum[(size_t)a * k + j] += sqrtf(gx * gx + gy * gy);
+				offset_denom[(size_t)a * k + j] += 1.f;
+			}
+		}
+	}
+	opacity_accum[a] += osum;
+	anchor_demon[a] += 1.f;
+}
+
 // ---- small helpers for the visible-anchor list ------------------------------------------------------------------------
 __global__ void mask_to_flags_kernel(int A, const uint8_t *__restrict__ mask, uint32_t *__restrict__ flags)
 {
@@ -639,6 +673,35 @@ cudaError_t decode_backward(const DecodeBwdArgs &a, cudaStream_t stream)
 	if ((e = set_smem(decode_backward_kernel, smem)) != cudaSuccess) return e;
 	// persistent; 2 CTAs/SM (102 KB of shared memory each at k = 10, 128 registers)
 	decode_backward_kernel<<<grid_for(a.f.n_vis, 2), 256, smem, stream>>>(a);
+	count_launch();
+	return cudaGetLastError();
+}
+
+size_t statis_scratch_bytes(int A, int k)
+{
+	const size_t a = (size_t)(A > 0 ? A : 1), n = a * (size_t)(k > 0 ? k : 1);
+	return 2 * align_up(a * 4) + 2 * align_up(n * 4) + scan_scratch_bytes((int64_t)n);
+}
+
+cudaError_t training_statis(int A, int k, int64_t n_vis, const uint8_t *anchor_visible, const uint8_t *offset_selected, const uint8_t *update_filter,
+                            const float *neural_opacity, const float *viewspace_grad, float *opacity_accum, float *anchor_demon,
+                            float *offset_gradient_accum, float *offset_denom, char *scratch, cudaStream_t stream)
+{
+	const size_t a = (size_t)A, n = (size_t)n_vis * k;
+	uint32_t *vflag = (uint32_t *)scratch, *vincl = (uint32_t *)(scratch + align_up(a * 4));
+	uint32_t *sflag = (uint32_t *)(scratch + 2 * align_up(a * 4)), *sincl = (uint32_t *)(scratch + 2 * align_up(a * 4) + align_up((size_t)A * k * 4));
+	char *tmp = scratch + 2 * align_up(a * 4) + 2 * align_up((size_t)A * k * 4);
+	cudaError_t e;
+	mask_to_flags_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, anchor_visible, vflag);
+	if ((e = inclusive_sum_gather(vflag, nullptr, vincl, A, tmp, stream)) != cudaSuccess) return e;
+	count_launch();
+	if (n > 0) {
+		mask_to_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)n, offset_selected, sflag);
+		if ((e = inclusive_sum_gather(sflag, nullptr, sincl, (int64_t)n, tmp, stream)) != cudaSuccess) return e;
+		count_launch();
+	}
+	training_statis_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, k, anchor_visible, vincl, offset_selected, sincl, update_filter, neural_opacity,
+	                                                          viewspace_grad, opacity_accum, anchor_demon, offset_gradient_accum, offset_denom);
 	count_launch();
 	return cudaGetLastError();
 }

@@ -189,6 +189,22 @@ GSR_API int gsr_decode_backward(
     float *g_anchor, float *g_feat, float *g_offset, float *g_scaling, float *const *g_mlp_params, gsr_stream_t stream);
 
 /*
+ * Densification statistics (first half) — replaces GaussianModel.training_statis
+ * (scene/gaussian_model.py:729-757): ~15 boolean-mask index kernels (each a host sync) become two scans and one kernel.
+ *   anchor_visible_mask[A], offset_selection_mask[n_vis*k] (= neural_opacity > 0), update_filter[P] (= radii > 0): bytes
+ *   neural_opacity[n_vis*k], viewspace_grad[P,3] (the .grad of render()'s screenspace_points = dL_dmeans2D)
+ *   in/out (fp32, updated in place): opacity_accum[A], anchor_demon[A], offset_gradient_accum[A*k], offset_denom[A*k]
+ *   scratch: gsr_training_statis_scratch_bytes(A, k).
+ */
+GSR_API size_t gsr_training_statis_scratch_bytes(int A, int n_offsets);
+GSR_API int gsr_training_statis(
+    int A, int n_offsets, int64_t n_vis, int64_t P,
+    const uint8_t *anchor_visible_mask, const uint8_t *offset_selection_mask, const uint8_t *update_filter,
+    const float *neural_opacity, const float *viewspace_grad,
+    float *opacity_accum, float *anchor_demon, float *offset_gradient_accum, float *offset_denom,
+    void *scratch, size_t scratch_bytes, gsr_stream_t stream);
+
+/*
  * Fused photometric loss, L1 + SSIM — replaces l1_loss / l1_loss_masked
  * (utils/loss_utils.py:27-31) and ssim / ssim_masked (utils/loss_utils.py:131-207, 11x11 Gaussian window, sigma 1.5,
  * zero padding, C1 = 0.01^2, C2 = 0.03^2, mean over all elements) as used by train.py:535-545.

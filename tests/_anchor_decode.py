@@ -94,6 +94,32 @@ def generate_neural_gaussians(camera_center, pc, visible_mask=None):
     return xyz, color, opacity, uncertainty, scaling, rot, neural_opacity, mask
 
 
+def init_statis_buffers(pc):
+    """scene/gaussian_model.py:84-95,316-320: the four densification-statistics buffers."""
+    A, k, dev = pc._anchor.shape[0], pc.n_offsets, pc._anchor.device
+    pc.opacity_accum = torch.zeros((A, 1), device=dev)
+    pc.anchor_demon = torch.zeros((A, 1), device=dev)
+    pc.offset_gradient_accum = torch.zeros((A * k, 1), device=dev)
+    pc.offset_denom = torch.zeros((A * k, 1), device=dev)
+
+
+def training_statis_eager(pc, viewspace_point_tensor, opacity, update_filter, offset_selection_mask, anchor_visible_mask):
+    """scene/gaussian_model.py:729-757 (GaussianModel.training_statis), the eager index code of the reference."""
+    temp_opacity = opacity.clone().view(-1).detach()
+    temp_opacity[temp_opacity < 0] = 0
+    temp_opacity = temp_opacity.view([-1, pc.n_offsets])
+    pc.opacity_accum[anchor_visible_mask] += temp_opacity.sum(dim=1, keepdim=True)
+    pc.anchor_demon[anchor_visible_mask] += 1
+    anchor_visible_mask = anchor_visible_mask.unsqueeze(dim=1).repeat([1, pc.n_offsets]).view(-1)
+    combined_mask = torch.zeros_like(pc.offset_gradient_accum, dtype=torch.bool).squeeze(dim=1)
+    combined_mask[anchor_visible_mask] = offset_selection_mask
+    temp_mask = combined_mask.clone()
+    combined_mask[temp_mask] = update_filter
+    grad_norm = torch.norm(viewspace_point_tensor.grad[update_filter, :2], dim=-1, keepdim=True)
+    pc.offset_gradient_accum[combined_mask] += grad_norm
+    pc.offset_denom[combined_mask] += 1
+
+
 def make_settings(mod, cam, bg, device):
     return mod.GaussianRasterizationSettings(
         image_height=cam["H"], image_width=cam["W"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg, scale_modifier=1.0,

@@ -5,12 +5,14 @@ SURVEY.md section 8d "Config 4").  One iteration = what train.py:497-603 does ar
     prefilter_voxel (visible_filter on the anchors)            gaussian_renderer/__init__.py:190-246
     generate_neural_gaussians + rasterize                       gaussian_renderer/__init__.py:104-179
     L1 + (1 - SSIM) on the image, scale/shift-aligned L1 depth  utils/loss_utils.py:27-28,80-110,131-164; train.py:535-560
-    scaling regulariser, backward, Adam step                    train.py:575-603
+    scaling regulariser, backward, densification statistics,    train.py:575-612, scene/gaussian_model.py:729-757
+    Adam step
 
 on a synthetic anchor model (10^5 anchors x 10 offsets, 1008x567) with synthetic target image / depth.  Both arms run
 this same file; they differ only in `decode` (torch restatement vs gscream_b200.decode) and `rast` (reference build vs
 gscream_b200.rasterizer).  The reference arm's losses are eager torch (its own code path); this repo's arm uses the fused L1 + SSIM kernel
-(gscream_b200.losses); the depth-alignment loss and the optimizer are plain torch on both sides.
+(gscream_b200.losses) and the fused densification statistics (gscream_b200.stats); the depth-alignment loss and the optimizer
+are plain torch on both sides.
 """
 import math
 
@@ -58,6 +60,7 @@ class TrainStep:
         from gscream_b200 import scenes
         self.mod, self.decode_fn, self.dev = rast_module, decode_fn, torch.device(device)
         self.fused_losses = fused_losses
+        self.fused_statis = fused_losses
         self.cam = scenes.make_camera(W, H)
         self.pc = ad.SyntheticAnchors(A, n_offsets=k, seed=seed, tanfov=(self.cam["tanfovx"], self.cam["tanfovy"])).to(self.dev)
         g = torch.Generator().manual_seed(seed + 1)
@@ -67,6 +70,7 @@ class TrainStep:
         self.valid = torch.ones(1, H, W, device=self.dev)
         self.window = _gaussian_window(device=self.dev)
         self.opt = torch.optim.Adam(self.pc.parameters(), lr=1e-4, eps=1e-15)
+        ad.init_statis_buffers(self.pc)
         self.campos = self.cam["campos"].to(self.dev)
         self.settings = ad.make_settings(self.mod, self.cam, self.bg, self.dev)
         self.last = {}
@@ -94,6 +98,12 @@ class TrainStep:
         loss = loss + 0.01 * scaling.prod(dim=1).mean()
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
+        with torch.no_grad():                                               # train.py:597-599
+            if self.fused_statis:
+                from gscream_b200 import stats
+                stats.training_statis(pc, ssp, nop, radii > 0, mask, vis)
+            else:
+                ad.training_statis_eager(pc, ssp, nop, radii > 0, mask, vis)
         self.opt.step()
         self.last = {"loss": loss.detach(), "P": xyz.shape[0], "n_vis": int(mask.shape[0] // pc.n_offsets)}
         return self.last
