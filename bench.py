@@ -341,8 +341,8 @@ def run_ours(args, cfg, rank, world, local):
             "roofline": {"bound": "hbm", "kernel": "gsr::blend_backward_kernel<%d>" % C, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of this
-                         # workload (profiles/r1_blend_v5_summary.md: 397.73 MB + 27.60 MB); config3 only
-                         "traffic": 425329664 if (args.workload == "config3" and args.scale_mult == 1.0) else None,
+                         # workload (profiles/r1_blend_v7_summary.md: 392.95 MB + 27.03 MB); config3 only
+                         "traffic": 419970304 if (args.workload == "config3" and args.scale_mult == 1.0) else None,
                          "algorithmic_bytes_per_launch": bytes_bwd,
                          "avg_launch_ms": t_bwd, "peak_source": peak_src,
                          "note": "blend kernels are FP32-issue bound, not HBM bound (see DESIGN.md / profiles/)"},

@@ -33,6 +33,7 @@ static_assert(kWarpsPerTile % GSR_FWD_WARPS_PER_CTA == 0 && kWarpsPerTile % GSR_
 constexpr int kChunk = 16;           // ring entries gathered / blended per pipeline step
 constexpr int kScan = 64;            // list entries scanned per refill (two per lane)
 constexpr int kRing = 128;           // ring capacity (>= kScan + 2 * kChunk + kChunk)
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= kScan + 3 * kChunk, "ring: power of two, holds one scan step plus the queued and in-flight chunks");
 constexpr uint32_t kIdMask = 0x00FFFFFFu;  // low 24 bits of a packed point_list entry: the Gaussian id
 constexpr float kAlphaMin = 1.0f / 255.0f;
 
