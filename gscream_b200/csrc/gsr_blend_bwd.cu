@@ -44,6 +44,14 @@
 #ifndef GSR_BWD_GCOL_SMEM
 #define GSR_BWD_GCOL_SMEM 0
 #endif
+// load the next entry's record (two LDS.128) one iteration ahead of its use: measured slower (2.32 vs 2.18 ms, 8 B of spill)
+#ifndef GSR_BWD_PREFETCH
+#define GSR_BWD_PREFETCH 0
+#endif
+// two partial sums in the lane = channel colour sums: -1 % (2.153 vs 2.178 ms); four (GSR_BWD_ACC4) are slower
+#ifndef GSR_BWD_PB2
+#define GSR_BWD_PB2 1
+#endif
 
 namespace gsr {
 
@@ -197,11 +205,22 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 		cp_async_wait_but_one();
 		__syncwarp(); // every lane's copies of this chunk have landed
 		const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
+#if GSR_BWD_PREFETCH
+		float4 r0n = *reinterpret_cast<const float4 *>(ent), r1n = *reinterpret_cast<const float4 *>(ent + 4);
+#endif
 		for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats) {
 			const uint32_t slot = (feed.done + e) & (kRing - 1);
 			const int pos = (int)feed.q_pos[slot]; // 0-based list position
+#if GSR_BWD_PREFETCH
+			const float4 r0 = r0n, r1 = r1n;     // this entry's record was loaded during the previous iteration
+			if (e + 1 < m_cur) {
+				r0n = *reinterpret_cast<const float4 *>(ent + TR::kEntryFloats);
+				r1n = *reinterpret_cast<const float4 *>(ent + TR::kEntryFloats + 4);
+			}
+#else
 			const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
 			const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
+#endif
 			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
 			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
 			const bool maybe = (pos < last_contributor) && !(power > 0.0f);
@@ -294,6 +313,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 				__syncwarp();
 #if GSR_BWD_ACC4
 				float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#elif GSR_BWD_PB2
+				float s0 = 0.f, s1 = 0.f;
+				float &s2 = s0, &s3 = s1;
 #else
 				float s0 = 0.f;
 				float &s1 = s0, &s2 = s0, &s3 = s0;
@@ -318,6 +340,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 				}
 #if GSR_BWD_ACC4
 				red_add(dL_dcolors + (size_t)id * C + lane, (s0 + s1) + (s2 + s3)); // 32 lanes -> one coalesced 128-B RED
+#elif GSR_BWD_PB2
+				red_add(dL_dcolors + (size_t)id * C + lane, s0 + s1);
 #else
 				red_add(dL_dcolors + (size_t)id * C + lane, s0);
 #endif

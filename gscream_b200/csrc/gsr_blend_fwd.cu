@@ -31,6 +31,10 @@ constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 
 // Resident CTAs per SM the register allocation must allow.  Measured (profiles/r1_occupancy_ab.md): the forward
 // kernel is latency bound, 4 CTAs/SM (64 registers) beats 3 CTAs/SM (80 registers) by 10 %.
+// the per-entry bit of the `blended` mask as a shifted loop variable instead of 1u << e: -1 % (0.880 vs 0.892 ms)
+#ifndef GSR_FWD_EBIT
+#define GSR_FWD_EBIT 1
+#endif
 #ifndef GSR_FWD_MINBLOCKS
 #define GSR_FWD_MINBLOCKS 4
 #endif
@@ -75,7 +79,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 			__syncwarp(); // every lane's copies of this chunk have landed
 			const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
 			uint32_t blended = 0; // bit e: this pixel blended entry e of the chunk
+#if GSR_FWD_EBIT
+			uint32_t ebit = 1u;
+			for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats, ebit <<= 1) {
+#else
 			for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats) {
+#endif
 				const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
 				const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
 				const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
@@ -110,7 +119,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 				UNC += r1.w * w;
 				T = test_T;
 				last_ring = feed.done + e + 1u;
+#if GSR_FWD_EBIT
+				blended |= ebit;
+#else
 				blended |= 1u << e;
+#endif
 			}
 			// Instances this warp examined but none of its 32 pixels blended: clear the warp's bit in the instance's mask, so that
 			// the backward pass (which scans the same list with the same masks) visits exactly the contributing (warp, instance) pairs
