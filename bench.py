@@ -398,8 +398,8 @@ def run_reference(args, cfg, rank, world, local):
 
 def run_train_step(args, rank, world, local):
     """BASELINE.json configs[3] substitute (SURVEY.md 8d "Config 4"): the train-step-equivalent loop of tests/_train_step.py,
-    1 GPU.  `--impl ours`: fused CUDA decode + this repo's rasterizer + fused L1/SSIM loss; `--impl reference`: torch decode (the reference's
-    generate_neural_gaussians restated) + the reference's own rasterizer build.  The aligned-depth loss and Adam are plain torch in both."""
+    1 GPU.  `--impl ours`: fused CUDA decode + this repo's rasterizer + fused L1/SSIM and aligned-depth losses + fused statistics; `--impl reference`: torch decode (the reference's
+    generate_neural_gaussians restated) + the reference's own rasterizer build.  Adam is plain torch in both."""
     if rank != 0:
         return None
     import _train_step as ts
@@ -424,7 +424,7 @@ def run_train_step(args, rank, world, local):
                                   "L1/SSIM/aligned-depth losses + densification statistics + Adam; P = %d Gaussians from %d visible anchors" % (A, k, W, H, loop.last["P"], loop.last["n_vis"]),
                       "decode": "fused CUDA (gsr_decode_*)" if args.impl == "ours" else "torch eager (reference code path)",
                       "rasterizer": "libgsr_b200" if args.impl == "ours" else "reference CUDA build (oracle/_ref/dgr3)",
-                      "losses": "fused L1 + SSIM (gsr_l1_ssim_*), eager aligned-depth loss and Adam" if args.impl == "ours" else "torch eager",
+                      "losses": "fused L1 + SSIM (gsr_l1_ssim_*) and aligned-depth L1 (gsr_depth_align_l1_*); Adam eager" if args.impl == "ours" else "torch eager",
                       "densification_statistics": "fused (gsr_training_statis)" if args.impl == "ours" else "torch eager (reference method)"},
            "clocks": clocks}
     if args.impl == "reference":

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "gsr_l1_ssim_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gsr_l1_ssim_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "gsr_debug_plain_point_list": (_i, [_i]),
+    "gsr_depth_align_l1_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsr_depth_align_l1_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_launch_count": (_i64, [_i]),
     "gsr_profile_enable": (_i, [_i]),
     "gsr_profile_read": (_i, [_i, _vp, _i]),

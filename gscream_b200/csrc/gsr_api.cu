@@ -451,6 +451,27 @@ int gsr_l1_ssim_backward(int planes, int height, int width, const float *taps11_
 	return 0;
 }
 
+int gsr_depth_align_l1_forward(int batch, int height, int width, const float *depth, const float *target, const float *fit_mask,
+                               const float *loss_mask, double *state, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (batch <= 0 || height <= 0 || width <= 0 || !depth || !target || !state) return GSR_E_BADARG;
+	StageTimer t(kLossFwd, stream);
+	GSR_CUDA(launch_depth_align_l1_forward(batch, height * width, depth, target, fit_mask, loss_mask, state + 1, state + 1 + 5 * batch, state, stream));
+	return 0;
+}
+
+int gsr_depth_align_l1_backward(int batch, int height, int width, const float *depth, const float *target, const float *fit_mask,
+                                const float *loss_mask, const double *state, const float *upstream, float *grad_depth, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (batch <= 0 || height <= 0 || width <= 0 || !depth || !target || !state || !upstream || !grad_depth) return GSR_E_BADARG;
+	StageTimer t(kLossBwd, stream);
+	GSR_CUDA(launch_depth_align_l1_backward(batch, height * width, depth, target, fit_mask, loss_mask, state + 1, state + 1 + 5 * batch, upstream,
+	                                        grad_depth, stream));
+	return 0;
+}
+
 int gsr_debug_export(int P, int64_t num_rendered, int width, int height, const void *geom_buffer, const void *binning_buffer,
                      const void *image_buffer, float *xy, float *depths, float *conic_opacity, uint32_t *tiles_touched,
                      uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib, gsr_stream_t stream_)

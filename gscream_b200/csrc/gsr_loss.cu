@@ -169,6 +169,106 @@ __global__ void __launch_bounds__(256) l1_ssim_backward_kernel(int H, int W, Tap
 	dx[pbase + pix] = gs * (c1 + 2.f * xv * c2 + yv * c3) + gl * sgn * wm;
 }
 
+
+// ---- scale / shift aligned depth L1 (train.py:548-569 with utils/loss_utils.py:80-102, 27-31) -----------------------------
+//   (s, t) = argmin sum_i m_i (s d_i + t - y_i)^2      closed form from five masked sums (compute_scale_and_shift)
+//   L      = mean_i( |abs(s) d_i + t - y_i| * lm_i )   l1_loss (lm = 1) or l1_loss_masked
+// The reference builds this from ~25 eager kernels and back-propagates through the closed form; here: one reduction for the
+// five sums, one for the loss (which also leaves the two sums the backward needs), one elementwise backward kernel.
+// The five sums are accumulated in fp64 and the 2x2 system is solved in fp64: det = a00 a11 - a01^2 cancels badly at image
+// sizes (both products ~1e13 for a 567x1008 depth map), where the reference's fp32 evaluation (utils/loss_utils.py:96-100) keeps
+// only ~3 digits of it; the result here is the exactly-rounded one, the reference's own fp32 deviation is what the tests allow for.
+__device__ __forceinline__ void solve_scale_shift(const double *sums, double &x0, double &x1, double &a00, double &a01, double &a11, double &det)
+{
+	a00 = sums[0]; a01 = sums[1]; a11 = sums[2];
+	const double b0 = sums[3], b1 = sums[4];
+	det = a00 * a11 - a01 * a01;
+	x0 = det != 0.0 ? (a11 * b0 - a01 * b1) / det : 0.0;
+	x1 = det != 0.0 ? (-a01 * b0 + a00 * b1) / det : 0.0;
+}
+__device__ __forceinline__ double block_sum_1d(float v, float *s_red)
+{
+#pragma unroll
+	for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double t = 0.0;
+	if (threadIdx.x == 0)
+		for (int w = 0; w < 8; w++) t += (double)s_red[w];
+	__syncthreads();
+	return t;
+}
+constexpr int kDepthItems = 8; // pixels per thread
+
+__global__ void __launch_bounds__(256) depth_fit_sums_kernel(int n, const float *__restrict__ d, const float *__restrict__ y,
+                                                             const float *__restrict__ m, double *__restrict__ sums)
+{
+	__shared__ float s_red[8];
+	const size_t base = (size_t)blockIdx.y * n;
+	float a00 = 0.f, a01 = 0.f, a11 = 0.f, b0 = 0.f, b1 = 0.f;
+	for (int k = 0; k < kDepthItems; k++) {
+		const int i = (blockIdx.x * kDepthItems + k) * 256 + threadIdx.x;
+		if (i < n) {
+			const float dv = d[base + i], yv = y[base + i], mv = m ? m[base + i] : 1.f;
+			a00 += mv * dv * dv; a01 += mv * dv; a11 += mv; b0 += mv * dv * yv; b1 += mv * yv;
+		}
+	}
+	double t;
+	t = block_sum_1d(a00, s_red); if (threadIdx.x == 0) atomicAdd(sums + blockIdx.y * 5 + 0, t);
+	t = block_sum_1d(a01, s_red); if (threadIdx.x == 0) atomicAdd(sums + blockIdx.y * 5 + 1, t);
+	t = block_sum_1d(a11, s_red); if (threadIdx.x == 0) atomicAdd(sums + blockIdx.y * 5 + 2, t);
+	t = block_sum_1d(b0, s_red);  if (threadIdx.x == 0) atomicAdd(sums + blockIdx.y * 5 + 3, t);
+	t = block_sum_1d(b1, s_red);  if (threadIdx.x == 0) atomicAdd(sums + blockIdx.y * 5 + 4, t);
+}
+
+__global__ void __launch_bounds__(256) depth_l1_kernel(int n, const float *__restrict__ d, const float *__restrict__ y,
+                                                       const float *__restrict__ lm, const double *__restrict__ sums,
+                                                       double *__restrict__ aux /*[B][2]: S1, S0*/, double *__restrict__ loss_sum)
+{
+	__shared__ float s_red[8];
+	const size_t base = (size_t)blockIdx.y * n;
+	double x0d, x1d, a00, a01, a11, det;
+	solve_scale_shift(sums + blockIdx.y * 5, x0d, x1d, a00, a01, a11, det);
+	const float sc = fabsf((float)x0d), x1 = (float)x1d;   // train.py:552 scale = torch.abs(scale)
+	float l = 0.f, s1 = 0.f, s0 = 0.f;
+	for (int k = 0; k < kDepthItems; k++) {
+		const int i = (blockIdx.x * kDepthItems + k) * 256 + threadIdx.x;
+		if (i < n) {
+			const float dv = d[base + i], w = lm ? lm[base + i] : 1.f;
+			const float r = sc * dv + x1 - y[base + i];
+			const float sg = (r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f)) * w;
+			l += fabsf(r) * w; s1 += sg * dv; s0 += sg;
+		}
+	}
+	double t;
+	t = block_sum_1d(l, s_red);  if (threadIdx.x == 0) atomicAdd(loss_sum, t);
+	t = block_sum_1d(s1, s_red); if (threadIdx.x == 0) atomicAdd(aux + blockIdx.y * 2 + 0, t);
+	t = block_sum_1d(s0, s_red); if (threadIdx.x == 0) atomicAdd(aux + blockIdx.y * 2 + 1, t);
+}
+
+__global__ void __launch_bounds__(256) depth_l1_backward_kernel(int n, float inv_total, const float *__restrict__ d, const float *__restrict__ y,
+                                                                const float *__restrict__ m, const float *__restrict__ lm,
+                                                                const double *__restrict__ sums, const double *__restrict__ aux,
+                                                                const float *__restrict__ upstream, float *__restrict__ dd)
+{
+	const size_t base = (size_t)blockIdx.y * n;
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	double x0d, x1d, a00, a01, a11, det;
+	solve_scale_shift(sums + blockIdx.y * 5, x0d, x1d, a00, a01, a11, det);
+	const float x0 = (float)x0d, x1 = (float)x1d, sc = fabsf(x0);
+	// dL/dx0 = sign(x0) * S1 / N, dL/dx1 = S0 / N; lambda = A^-1 (dL/dx0, dL/dx1), in fp64 for the same cancellation reason
+	const double g0 = (x0d > 0.0 ? 1.0 : (x0d < 0.0 ? -1.0 : 0.0)) * aux[blockIdx.y * 2 + 0] * (double)inv_total;
+	const double g1 = aux[blockIdx.y * 2 + 1] * (double)inv_total;
+	const float l0 = det != 0.0 ? (float)((a11 * g0 - a01 * g1) / det) : 0.f;
+	const float l1 = det != 0.0 ? (float)((-a01 * g0 + a00 * g1) / det) : 0.f;
+	const float dv = d[base + i], yv = y[base + i];
+	const float mv = m ? m[base + i] : 1.f, w = lm ? lm[base + i] : 1.f;
+	const float r = sc * dv + x1 - yv;
+	const float sg = (r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f)) * w;
+	dd[base + i] = __ldg(upstream) * (sg * sc * inv_total + mv * (l0 * (yv - 2.f * dv * x0 - x1) - l1 * x0));
+}
+
 } // namespace
 
 cudaError_t launch_l1_ssim_forward(int planes, int H, int W, const float *taps11, const float *x, const float *y, const float *mask,
@@ -193,6 +293,29 @@ cudaError_t launch_l1_ssim_backward(int planes, int H, int W, const float *taps1
 	dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, planes), block(kT, kT);
 	l1_ssim_backward_kernel<<<grid, block, 0, stream>>>(H, W, t, x, y, mask, mask_planes, p1, p2, p3, upstream,
 	                                                   1.0f / ((float)planes * (float)H * (float)W), dx);
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_depth_align_l1_forward(int B, int n, const float *d, const float *y, const float *fit_mask, const float *loss_mask,
+                                          double *sums, double *aux, double *loss_sum, cudaStream_t stream)
+{
+	cudaError_t e;
+	if ((e = cudaMemsetAsync(sums, 0, (size_t)B * 5 * sizeof(double), stream)) != cudaSuccess) return e;
+	if ((e = cudaMemsetAsync(aux, 0, (size_t)B * 2 * sizeof(double), stream)) != cudaSuccess) return e;
+	if ((e = cudaMemsetAsync(loss_sum, 0, sizeof(double), stream)) != cudaSuccess) return e;
+	dim3 grid((n + 256 * kDepthItems - 1) / (256 * kDepthItems), B);
+	depth_fit_sums_kernel<<<grid, 256, 0, stream>>>(n, d, y, fit_mask, sums);
+	depth_l1_kernel<<<grid, 256, 0, stream>>>(n, d, y, loss_mask, sums, aux, loss_sum);
+	count_launch(5);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_depth_align_l1_backward(int B, int n, const float *d, const float *y, const float *fit_mask, const float *loss_mask,
+                                           const double *sums, const double *aux, const float *upstream, float *dd, cudaStream_t stream)
+{
+	dim3 grid((n + 255) / 256, B);
+	depth_l1_backward_kernel<<<grid, 256, 0, stream>>>(n, 1.0f / ((float)B * (float)n), d, y, fit_mask, loss_mask, sums, aux, upstream, dd);
 	count_launch();
 	return cudaGetLastError();
 }

@@ -14,4 +14,11 @@ cudaError_t launch_l1_ssim_backward(int planes, int H, int W, const float *taps1
                                     int mask_planes, const float *p1, const float *p2, const float *p3, const float *upstream, float *dx,
                                     cudaStream_t stream);
 
+// Scale / shift aligned depth L1.  d, y (and the optional masks) are [B][n]; sums fp64[B][5], aux fp64[B][2], loss_sum fp64[1]
+// (all device, written by the forward, read by the backward); upstream: device fp32 scalar dL/dloss; dd [B][n] is overwritten.
+cudaError_t launch_depth_align_l1_forward(int B, int n, const float *d, const float *y, const float *fit_mask, const float *loss_mask,
+                                          double *sums, double *aux, double *loss_sum, cudaStream_t stream);
+cudaError_t launch_depth_align_l1_backward(int B, int n, const float *d, const float *y, const float *fit_mask, const float *loss_mask,
+                                           const double *sums, const double *aux, const float *upstream, float *dd, cudaStream_t stream);
+
 } // namespace gsr

@@ -3,7 +3,8 @@ utils/loss_utils.py (:27-31, :131-207), SURVEY.md section 8f rank 3.
 
 Same names, argument order and return values (0-d tensors) as the reference functions, so train.py:535-545 can import them
 from here instead; `l1_ssim(image, gt, mask)` returns both means from ONE forward / ONE backward kernel
-(`gsr_l1_ssim_forward/backward` of include/gsr_b200.h), which is what the train-step loop of bench.py uses.
+(`gsr_l1_ssim_forward/backward` of include/gsr_b200.h), which is what the train-step loop of bench.py uses;
+`aligned_depth_l1(depth, target, fit_mask, loss_mask)` is the scale/shift-aligned depth L1 of train.py:548-569.
 Only the rendered image receives a gradient (the target and the mask are data).  No CPU / eager fallback: CPU tensors raise.
 """
 from math import exp
@@ -76,6 +77,58 @@ class _L1SSIM(torch.autograd.Function):
                                                 m.data_ptr() if m.numel() else None, mp, partials.data_ptr(), ups.data_ptr(),
                                                 grad.data_ptr(), torch.cuda.current_stream().cuda_stream))
         return grad.view(shape), None, None
+
+
+class _AlignedDepthL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, target, fit_mask, loss_mask):
+        lib = _lib.load()
+        d, B, H, W = _planes(depth, "depth")
+        y, By, Hy, Wy = _planes(target, "target")
+        if (By, Hy, Wy) != (B, H, W):
+            raise ValueError("depth and target shapes differ: %s vs %s" % (tuple(depth.shape), tuple(target.shape)))
+        masks = []
+        for m, name in ((fit_mask, "fit_mask"), (loss_mask, "loss_mask")):
+            if m is None:
+                masks.append(None)
+                continue
+            mm, Bm, Hm, Wm = _planes(m.to(torch.float32) if m.dtype != torch.float32 else m, name)
+            if (Bm, Hm, Wm) != (B, H, W):
+                raise ValueError("%s must have the shape of depth" % name)
+            masks.append(mm)
+        dev = d.device
+        state = torch.empty(1 + 7 * B, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gsr_depth_align_l1_forward(B, H, W, d.data_ptr(), y.data_ptr(), masks[0].data_ptr() if masks[0] is not None else None,
+                                                      masks[1].data_ptr() if masks[1] is not None else None, state.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream))
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(d, y, masks[0] if masks[0] is not None else empty, masks[1] if masks[1] is not None else empty, state)
+        ctx.dims = (B, H, W, tuple(depth.shape))
+        return (state[0] / float(B * H * W)).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        d, y, fm, lm, state = ctx.saved_tensors
+        B, H, W, shape = ctx.dims
+        up = g.to(torch.float32).reshape(1).contiguous()
+        grad = torch.empty((B, H, W), dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            _lib.check(lib.gsr_depth_align_l1_backward(B, H, W, d.data_ptr(), y.data_ptr(), fm.data_ptr() if fm.numel() else None,
+                                                       lm.data_ptr() if lm.numel() else None, state.data_ptr(), up.data_ptr(), grad.data_ptr(),
+                                                       torch.cuda.current_stream().cuda_stream))
+        return grad.view(shape), None, None, None
+
+
+def aligned_depth_l1(depth, target, fit_mask=None, loss_mask=None):
+    """train.py:548-555 / 563-569 in one node: `scale, shift = compute_scale_and_shift(depth, target, fit_mask)`
+    (utils/loss_utils.py:80-102), `scale = torch.abs(scale)`, `aligned = scale * depth + shift`, then `l1_loss(aligned, target)`
+    (loss_mask None) or `l1_loss_masked(aligned, target, loss_mask)`; the gradient flows through the closed-form fit like the
+    reference's.  depth / target / masks: [B, H, W] (B = 1 in train.py)."""
+    if target.requires_grad:
+        raise NotImplementedError("fused aligned_depth_l1 differentiates w.r.t. the rendered depth only")
+    return _AlignedDepthL1.apply(depth, target, fit_mask, loss_mask)
 
 
 def l1_ssim(image, gt, mask=None):

@@ -226,6 +226,22 @@ GSR_API int gsr_l1_ssim_backward(
     const float *partials, const float *upstream, float *grad_image, gsr_stream_t stream);
 
 /*
+ * Scale / shift aligned depth L1 — replaces compute_scale_and_shift
+ * (utils/loss_utils.py:80-102) + torch.abs(scale) + l1_loss / l1_loss_masked on the aligned depth as train.py:548-569 combines
+ * them, including the gradient through the closed-form fit.
+ *   depth, target, fit_mask (NULL = ones), loss_mask (NULL = l1_loss, else l1_loss_masked): [batch, H, W]
+ *   state: DEVICE fp64[1 + 7 * batch]: [0] = sum(|abs(s) depth + t - target| * loss_mask) over the whole batch (divide by
+ *          batch*H*W for the reference's mean), then the five fit sums and two backward sums per image.
+ * backward: upstream = DEVICE fp32 scalar dL/d(mean); grad_depth [batch, H, W] is overwritten.
+ */
+GSR_API int gsr_depth_align_l1_forward(
+    int batch, int height, int width, const float *depth, const float *target, const float *fit_mask, const float *loss_mask,
+    double *state, gsr_stream_t stream);
+GSR_API int gsr_depth_align_l1_backward(
+    int batch, int height, int width, const float *depth, const float *target, const float *fit_mask, const float *loss_mask,
+    const double *state, const float *upstream, float *grad_depth, gsr_stream_t stream);
+
+/*
  * Introspection for parity tests (device -> device copies out of the private scratch layout).
  * Any output pointer may be NULL.  Shapes: xy[P,2] depths[P] conic_opacity[P,4]
  * tiles_touched[P] point_list[R] ranges[tiles,2] final_T[H*W] n_contrib[H*W].

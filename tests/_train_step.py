@@ -10,9 +10,8 @@ SURVEY.md section 8d "Config 4").  One iteration = what train.py:497-603 does ar
 
 on a synthetic anchor model (10^5 anchors x 10 offsets, 1008x567) with synthetic target image / depth.  Both arms run
 this same file; they differ only in `decode` (torch restatement vs gscream_b200.decode) and `rast` (reference build vs
-gscream_b200.rasterizer).  The reference arm's losses are eager torch (its own code path); this repo's arm uses the fused L1 + SSIM kernel
-(gscream_b200.losses) and the fused densification statistics (gscream_b200.stats); the depth-alignment loss and the optimizer
-are plain torch on both sides.
+gscream_b200.rasterizer).  The reference arm's losses are eager torch (its own code path); this repo's arm uses the fused L1 + SSIM and aligned-depth-L1
+kernels (gscream_b200.losses) and the fused densification statistics (gscream_b200.stats); the optimizer is plain torch on both sides.
 """
 import math
 
@@ -92,9 +91,12 @@ class TrainStep:
         else:
             l1 = (image - self.target).abs().mean()
             loss = 0.8 * l1 + 0.2 * (1.0 - ssim(image, self.target, self.window))
-        s, t = compute_scale_and_shift(depth, self.target_depth, self.valid)
-        aligned = s.abs().view(-1, 1, 1) * depth + t.view(-1, 1, 1)
-        loss = loss + 0.1 * (aligned - self.target_depth).abs().mean()
+        if self.fused_losses:
+            loss = loss + 0.1 * losses.aligned_depth_l1(depth, self.target_depth, self.valid)   # gsr_depth_align_l1_*
+        else:
+            s, t = compute_scale_and_shift(depth, self.target_depth, self.valid)
+            aligned = s.abs().view(-1, 1, 1) * depth + t.view(-1, 1, 1)
+            loss = loss + 0.1 * (aligned - self.target_depth).abs().mean()
         loss = loss + 0.01 * scaling.prod(dim=1).mean()
         self.opt.zero_grad(set_to_none=True)
         loss.backward()

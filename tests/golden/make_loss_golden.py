@@ -17,7 +17,7 @@ from torch.autograd import Variable
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/utils/loss_utils.py"
-NAMES = ("l1_loss", "l1_loss_masked", "gaussian", "create_window", "ssim", "_ssim", "ssim_masked", "_ssim_masked")
+NAMES = ("l1_loss", "l1_loss_masked", "gaussian", "create_window", "ssim", "_ssim", "ssim_masked", "_ssim_masked", "compute_scale_and_shift")
 
 
 def reference_functions():
@@ -53,7 +53,35 @@ def run_case(C, H, W, seed, masked, mask_planes, dtype):
                 ssim=s.detach().numpy(), l1=l.detach().numpy(), g_ssim=gs.numpy(), g_l1=gl.numpy())
 
 
+def run_depth_case(B, H, W, seed, masked_fit, masked_loss, dtype):
+    """train.py:548-555 (reference view: fit on the valid mask, unmasked L1) and :563-569 (other views: masked L1)."""
+    ns = reference_functions()
+    g = torch.Generator().manual_seed(seed)
+    depth = 2.0 + 6.0 * torch.rand(B, H, W, generator=g)
+    target = (0.7 * depth + 1.3 + 0.4 * torch.randn(B, H, W, generator=g)).clamp(min=0.1)
+    fit = (torch.rand(B, H, W, generator=g) > 0.25).float() if masked_fit else None
+    x = depth.to(dtype).clone().requires_grad_(True)
+    y = target.to(dtype)
+    fm = None if fit is None else fit.to(dtype)
+    scale, shift = ns["compute_scale_and_shift"](x, y, fm)
+    scale = torch.abs(scale)
+    aligned = scale.view(-1, 1, 1) * x + shift.view(-1, 1, 1)
+    loss = ns["l1_loss_masked"](aligned, y, fm) if masked_loss else ns["l1_loss"](aligned, y)
+    gr, = torch.autograd.grad(loss, x)
+    return dict(depth=depth.numpy(), target=target.numpy(), fit=np.zeros(0, np.float32) if fit is None else fit.numpy(),
+                masked_loss=int(masked_loss), loss=loss.detach().numpy(), scale=scale.detach().numpy(), shift=shift.detach().numpy(), grad=gr.numpy())
+
+
 if __name__ == "__main__":
+    for name, (B, H, W, seed, mf, ml) in {"depth_ref_view": (1, 61, 83, 21, True, False), "depth_other_view": (1, 40, 56, 22, True, True),
+                                           "depth_nomask_b2": (2, 17, 23, 23, False, False)}.items():
+        r32 = run_depth_case(B, H, W, seed, mf, ml, torch.float32)
+        r64 = run_depth_case(B, H, W, seed, mf, ml, torch.float64)
+        out = dict(r32)
+        for k in ("loss", "scale", "shift", "grad"):
+            out["f64." + k] = r64[k]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "loss %.6f scale %s shift %s" % (float(r32["loss"]), r32["scale"], r32["shift"]))
     cases = {"loss_rgb": (3, 70, 101, 5, False, 0), "loss_rgb_masked1": (3, 64, 48, 6, True, 1), "loss_rgb_masked3": (3, 33, 57, 7, True, 3),
              "loss_tiny": (1, 7, 9, 8, False, 0)}
     for name, (C, H, W, seed, masked, mp) in cases.items():

@@ -102,3 +102,55 @@ def test_gpu_losses_train_step_size_vs_fp64_restatement():
     sb, lb = losses.l1_ssim(xb, yb)
     assert abs(float(sb) - float(s64)) <= 2e-5 * abs(float(s64))   # SSIM and L1 are symmetric in (x, y)
     assert abs(float(lb) - float(l64)) <= 2e-5 * abs(float(l64))
+
+
+# ---- scale / shift aligned depth L1 -------------------------------------------------------------------------------
+DEPTH_GOLDEN = ("depth_ref_view", "depth_other_view", "depth_nomask_b2")
+
+
+@pytest.mark.parametrize("name", DEPTH_GOLDEN)
+def test_restatement_of_scale_and_shift_matches_reference(golden_dir, name):
+    """Pins tests/_train_step.compute_scale_and_shift (the eager depth term of bench.py's reference arm) to the reference's."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    d, y = torch.from_numpy(z["depth"]), torch.from_numpy(z["target"])
+    m = torch.ones_like(d) if z["fit"].size == 0 else torch.from_numpy(z["fit"])
+    s, t = ts.compute_scale_and_shift(d, y, m)
+    np.testing.assert_allclose(s.abs().numpy(), z["scale"], rtol=1e-6)
+    np.testing.assert_allclose(t.numpy(), z["shift"], rtol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DEPTH_GOLDEN)
+def test_gpu_aligned_depth_l1_matches_reference_golden(golden_dir, name):
+    from gscream_b200 import losses
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    dev = torch.device("cuda")
+    d = torch.from_numpy(z["depth"]).to(dev).requires_grad_(True)
+    y = torch.from_numpy(z["target"]).to(dev)
+    fit = None if z["fit"].size == 0 else torch.from_numpy(z["fit"]).to(dev)
+    loss = losses.aligned_depth_l1(d, y, fit, fit if int(z["masked_loss"]) else None)
+    g, = torch.autograd.grad(3.0 * loss, d)            # a non-trivial upstream factor
+    assert abs(float(loss) - float(z["f64.loss"])) <= 1e-5 * abs(float(z["f64.loss"]))
+    ref = 3.0 * z["f64.grad"]
+    extra = 6.0 * float(np.abs(z["grad"] - z["f64.grad"]).max())
+    _close(g.cpu().numpy().astype(np.float64), ref, 1e-5, "d loss / d depth", extra=extra)
+
+
+@pytest.mark.gpu
+def test_gpu_aligned_depth_l1_train_step_size_vs_fp64():
+    from gscream_b200 import losses
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(8)
+    H, W = 567, 1008
+    depth = 2.0 + 8.0 * torch.rand(1, H, W, generator=g)
+    target = 2.0 + 10.0 * torch.rand(1, H, W, generator=g)
+    valid = (torch.rand(1, H, W, generator=g) > 0.1).float()
+    x64 = depth.double().to(dev).requires_grad_(True)
+    s, t = ts.compute_scale_and_shift(x64, target.double().to(dev), valid.double().to(dev))
+    l64 = (s.abs().view(-1, 1, 1) * x64 + t.view(-1, 1, 1) - target.double().to(dev)).abs().mean()
+    g64, = torch.autograd.grad(l64, x64)
+    x = depth.to(dev).requires_grad_(True)
+    l = losses.aligned_depth_l1(x, target.to(dev), valid.to(dev))
+    l.backward()
+    assert abs(float(l) - float(l64)) <= 1e-5 * abs(float(l64))
+    _close(x.grad.double().cpu().numpy(), g64.cpu().numpy(), 2e-5, "aligned depth gradient at train-step size")
