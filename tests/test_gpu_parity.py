@@ -109,6 +109,13 @@ ORACLE_KEY = {"dL_dmeans3D": "dL_dmeans3D", "dL_dmeans2D": "dL_dmean2D", "dL_dco
     (1500, 97, 65, 32, 104, 4.0, -9.0),      # ragged, long lists (several 256-batches per tile)
     (1, 64, 64, 3, 105, 6.0, 0.0),           # a single Gaussian
     (300, 16, 16, 32, 106, 2.0, 0.0),        # a single tile
+    # warp-feed corner cases: lists longer than the 128-entry ring with nearly every entry a hit, images smaller than a tile /
+    # than one warp's 8x4 block, a one-pixel image, a one-row strip (most warps of every tile have no pixel at all)
+    (900, 16, 16, 32, 107, 12.0, 0.0),
+    (600, 7, 3, 3, 108, 6.0, 0.0),
+    (40, 1, 1, 32, 109, 8.0, 0.0),
+    (2500, 333, 1, 32, 110, 3.0, 0.0),
+    (1200, 19, 45, 3, 111, 9.0, 5.0),
 ])
 def test_against_cpu_oracle(P, W, H, C, seed, smult, yaw):
     _require_native()
