@@ -104,6 +104,8 @@ __device__ __forceinline__ bool vowner(int lane)
 #define GSR_BWD_GCOL_WARPS 20
 #endif
 #define GSR_BWD_MINCTAS(C) ((C) == 32 ? (GSR_BWD_GCOL_WARPS / kWarpsPerCta) : GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
+#elif defined(GSR_BWD_MINCTAS32)
+#define GSR_BWD_MINCTAS(C) ((C) == 32 ? GSR_BWD_MINCTAS32 : GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
 #else
 #define GSR_BWD_MINCTAS(C) (GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
 #endif
