@@ -61,10 +61,15 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // One warp's feed over its tile's list.  kReverse: scan back to front starting at list position n-1 (backward pass).
+// kBulk (C > 3 only): the 128-B feature rows travel by one cp.async.bulk (TMA, SASS UBLKCP) per entry, issued by the lane that
+// owns the entry and completing on the stage's mbarrier; records stay on 16-B cp.async.  The async proxy keeps the feature
+// traffic off the LSU pipe at the price of one serialised issue round per entry (A/B: profiles/r1_feed_ab.md section 6).
 // All members are warp-uniform except `lane`-dependent temporaries.
-template <int C, bool kReverse>
+template <int C, bool kReverse, bool kBulk = false>
 struct WarpFeed {
 	using TR = BlendTraits<C>;
+	static constexpr int kExtraBytes = kBulk ? 16 : 0;   // two mbarriers behind the ring
+	uint64_t *bars;
 	const uint32_t *list;      // point_list + range.x
 	const float *rec, *feat;
 	float *stage;              // [2][kChunk][kEntryFloats]
@@ -85,6 +90,16 @@ struct WarpFeed {
 		stage = reinterpret_cast<float *>(warp_smem);
 		q_id = reinterpret_cast<uint32_t *>(warp_smem + 2 * TR::kStageFloats * 4);
 		q_pos = q_id + kRing;
+		if constexpr (kBulk) {
+			static_assert(!kBulk || !TR::kFeatInRec, "bulk feature rows need C > 3");
+			bars = reinterpret_cast<uint64_t *>(q_pos + kRing);
+			if (lane_ == 0) {
+				mbar_init(&bars[0], 1);
+				mbar_init(&bars[1], 1);
+				mbar_fence_init();
+			}
+			__syncwarp();
+		}
 		list = list_; n = n_; rec = rec_; feat = feat_; warp = warp_; lane = lane_; packed = packed_;
 		next_scan = 0;
 		tail = issued = done = 0;
@@ -139,7 +154,12 @@ struct WarpFeed {
 					cp_async16(dst + e * TR::kEntryFloats + part * 4, rec + (size_t)q_id[(issued + e) & (kRing - 1)] * GSR_REC_FLOATS + part * 4);
 			}
 		}
-		if constexpr (!TR::kFeatInRec) {
+		if constexpr (kBulk) {
+			if (m > 0) {
+				if (lane == 0) mbar_arrive_expect_tx(&bars[s], (uint32_t)m * C * 4);
+				if (lane < m) bulk_g2s(dst + lane * TR::kEntryFloats + TR::kRecParts * 4, feat + (size_t)q_id[(issued + lane) & (kRing - 1)] * C, C * 4, &bars[s]);
+			}
+		} else if constexpr (!TR::kFeatInRec) {
 			constexpr int kPer = 32 / TR::kFeatParts;
 			static_assert(32 % TR::kFeatParts == 0, "feature row must split into a power-of-two number of 16-B parts");
 			const int le = lane / TR::kFeatParts, part = lane % TR::kFeatParts;
@@ -153,6 +173,20 @@ struct WarpFeed {
 		cp_async_commit();
 		issued += m;
 		return m;
+	}
+	// chunk number `chunk` (m entries, gathered into stage chunk & 1) has landed for this lane; one more chunk may be in flight
+	__device__ __forceinline__ void wait(int chunk, int m)
+	{
+		cp_async_wait_but_one();
+		if constexpr (kBulk)
+			if (m > 0) mbar_wait(&bars[chunk & 1], (uint32_t)((chunk >> 1) & 1));
+	}
+	// before the warp retires: nothing may still be in flight into its shared memory (`m_pending` entries of chunk `chunk`)
+	__device__ __forceinline__ void drain(int chunk, int m_pending)
+	{
+		cp_async_wait_all();
+		if constexpr (kBulk)
+			if (m_pending > 0) mbar_wait(&bars[chunk & 1], (uint32_t)((chunk >> 1) & 1));
 	}
 };
 

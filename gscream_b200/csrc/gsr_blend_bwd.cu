@@ -96,6 +96,10 @@ __device__ __forceinline__ bool vowner(int lane)
 
 // C = 32 keeps a 34-float gradient row and a 32-float gradient column per lane: 124 registers, 2 CTAs/SM (forcing 3
 // spills 108 B and is 18 % slower, profiles/r1_occupancy_ab.md).  Small C fits 3.
+// feature rows by per-entry TMA bulk copies instead of 16-B cp.async (C = 32): A/B in profiles/r1_feed_ab.md section 6
+#ifndef GSR_BWD_FEED_BULK
+#define GSR_BWD_FEED_BULK 0
+#endif
 #ifndef GSR_BWD_MINBLOCKS
 #define GSR_BWD_MINBLOCKS(C) ((C) <= 8 ? 3 : 2)
 #endif
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 	}
 	// role switch (C == 32): lane l also holds channel l's gradient for the warp's 32 pixels
 	float gcol[(kLaneChannel && !kGcolSmem) ? 32 : 1];
-	float *s_gc = reinterpret_cast<float *>(smem_raw + (size_t)kWarpsPerCta * TR::kWarpBytes) + lwarp * 32 * kGcolStride; // [ch][36]
+	float *s_gc = reinterpret_cast<float *>(smem_raw + (size_t)kWarpsPerCta * (TR::kWarpBytes + ((GSR_BWD_FEED_BULK != 0 && C > 3) ? 16 : 0))) + lwarp * 32 * kGcolStride; // [ch][36]
 	if (kGcolSmem) {
 #pragma unroll
 		for (int ch = 0; ch < C; ch++) s_gc[ch * kGcolStride + lane] = g[ch];
@@ -197,14 +201,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 	const float neg_Tfinal_bg = -T_final * bg_dot; // background term: (-T_final / (1 - alpha)) * sum_ch bg[ch] g[ch]
 
 	// back to front (CR/backward.cu:500): the feed scans list positions warp_last-1 .. 0
-	WarpFeed<C, true> feed;
-	feed.init(smem_raw + (size_t)lwarp * TR::kWarpBytes, point_list + range.x, warp_last, rec, features, warp, lane, packed != 0);
+	using Feed = WarpFeed<C, true, (GSR_BWD_FEED_BULK != 0) && (C > 3)>;
+	Feed feed;
+	feed.init(smem_raw + (size_t)lwarp * (TR::kWarpBytes + Feed::kExtraBytes), point_list + range.x, warp_last, rec, features, warp, lane, packed != 0);
 	feed.fill();
 	int m_cur = feed.issue(0);
-	for (int chunk = 0; m_cur > 0; chunk++) {
+	int chunk = 0;
+	for (; m_cur > 0; chunk++) {
 		feed.fill();
 		const int m_next = feed.issue((chunk + 1) & 1);
-		cp_async_wait_but_one();
+		feed.wait(chunk, m_cur);
 		__syncwarp(); // every lane's copies of this chunk have landed
 		const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
 #if GSR_BWD_PREFETCH
@@ -354,13 +360,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 		__syncwarp(); // the stage buffer and the ring slots of this chunk may be reused
 		m_cur = m_next;
 	}
-	cp_async_wait_all();
+	feed.drain(chunk, 0);
 }
 
 template <int C>
 static size_t bwd_smem_bytes()
 {
-	return (size_t)kWarpsPerCta * (BlendTraits<C>::kWarpBytes + ((C == 32 && GSR_BWD_GCOL_SMEM) ? 32 * 36 * 4 : 0));
+	return (size_t)kWarpsPerCta * (BlendTraits<C>::kWarpBytes + ((GSR_BWD_FEED_BULK != 0 && C > 3) ? 16 : 0) + ((C == 32 && GSR_BWD_GCOL_SMEM) ? 32 * 36 * 4 : 0));
 }
 
 template <int C>

@@ -35,6 +35,10 @@ constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 #ifndef GSR_FWD_EBIT
 #define GSR_FWD_EBIT 1
 #endif
+// feature rows by per-entry TMA bulk copies instead of 16-B cp.async (C = 32): A/B in profiles/r1_feed_ab.md section 6
+#ifndef GSR_FWD_FEED_BULK
+#define GSR_FWD_FEED_BULK 0
+#endif
 #ifndef GSR_FWD_MINBLOCKS
 #define GSR_FWD_MINBLOCKS 4
 #endif
@@ -68,14 +72,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 	bool done = !inside;
 
 	if (!__all_sync(0xffffffffu, done)) {
-		WarpFeed<C, false> feed;
-		feed.init(smem_raw + (size_t)lwarp * TR::kWarpBytes, point_list + range.x, (int)(range.y - range.x), rec, features, warp, lane, packed != 0);
+		using Feed = WarpFeed<C, false, (GSR_FWD_FEED_BULK != 0) && (C > 3)>;
+		Feed feed;
+		feed.init(smem_raw + (size_t)lwarp * (TR::kWarpBytes + Feed::kExtraBytes), point_list + range.x, (int)(range.y - range.x), rec, features, warp, lane, packed != 0);
 		feed.fill();
 		int m_cur = feed.issue(0);
-		for (int chunk = 0; m_cur > 0; chunk++) {
+		int chunk = 0;
+		for (; m_cur > 0; chunk++) {
 			feed.fill();
 			const int m_next = feed.issue((chunk + 1) & 1);
-			cp_async_wait_but_one();
+			feed.wait(chunk, m_cur);
 			__syncwarp(); // every lane's copies of this chunk have landed
 			const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
 			uint32_t blended = 0; // bit e: this pixel blended entry e of the chunk
@@ -137,9 +143,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 			feed.done += m_cur;
 			__syncwarp(); // the stage buffer and the ring slots of this chunk may be reused
 			m_cur = m_next;
-			if (__all_sync(0xffffffffu, done)) break; // this warp's 32 pixels are saturated
+			if (__all_sync(0xffffffffu, done)) { chunk++; break; } // this warp's 32 pixels are saturated; chunk `chunk` may be in flight
 		}
-		cp_async_wait_all(); // nothing may be in flight into shared memory when the warp retires
+		feed.drain(chunk, m_cur); // nothing may be in flight into shared memory when the warp retires
 	}
 
 	if (inside) {
@@ -324,6 +330,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MMA_MINWARPS / kWar
 }
 
 template <int C>
+static size_t fwd_smem_bytes()
+{
+	return (size_t)kWarpsPerCta * (BlendTraits<C>::kWarpBytes + ((GSR_FWD_FEED_BULK != 0 && C > 3) ? 16 : 0));
+}
+
+template <int C>
 static cudaError_t launch_fwd(int tiles, const uint2 *ranges, uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
                               const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
                               float *out_depth, float *out_unc, cudaStream_t stream)
@@ -331,11 +343,11 @@ static cudaError_t launch_fwd(int tiles, const uint2 *ranges, uint32_t *point_li
 	using TR = BlendTraits<C>;
 	static bool configured = false;
 	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(blend_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t)kWarpsPerCta * TR::kWarpBytes);
+		cudaError_t e = cudaFuncSetAttribute(blend_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<C>());
 		if (e != cudaSuccess) return e;
 		configured = true;
 	}
-	blend_forward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * TR::kWarpBytes, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_T, n_contrib,
+	blend_forward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, fwd_smem_bytes<C>(), stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_T, n_contrib,
 	                                                               out_color, out_depth, out_unc);
 	count_launch();
 	return cudaGetLastError();
