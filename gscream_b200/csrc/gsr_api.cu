@@ -472,6 +472,29 @@ int gsr_depth_align_l1_backward(int batch, int height, int width, const float *d
 	return 0;
 }
 
+int gsr_depth_grad_forward(int batch, int height, int width, int n_scales, const float *prediction, const float *target, const float *mask,
+                           const double *fit_state, double *gstate, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (batch <= 0 || height <= 0 || width <= 0 || n_scales < 1 || n_scales > 4 || !prediction || !target || !gstate) return GSR_E_BADARG;
+	StageTimer t(kLossFwd, stream);
+	GSR_CUDA(launch_depth_grad_forward(batch, height, width, n_scales, prediction, target, mask, fit_state ? fit_state + 1 : nullptr, gstate, stream));
+	return 0;
+}
+
+int gsr_depth_grad_backward(int batch, int height, int width, int n_scales, const float *prediction, const float *target, const float *mask,
+                            const float *fit_mask, const double *fit_state, const double *gstate, const float *upstream, float *grad,
+                            int accumulate, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (batch <= 0 || height <= 0 || width <= 0 || n_scales < 1 || n_scales > 4 || !prediction || !target || !gstate || !upstream || !grad)
+		return GSR_E_BADARG;
+	StageTimer t(kLossBwd, stream);
+	GSR_CUDA(launch_depth_grad_backward(batch, height, width, n_scales, prediction, target, mask, fit_mask, fit_state ? fit_state + 1 : nullptr,
+	                                    gstate, upstream, grad, accumulate, stream));
+	return 0;
+}
+
 int gsr_debug_export(int P, int64_t num_rendered, int width, int height, const void *geom_buffer, const void *binning_buffer,
                      const void *image_buffer, float *xy, float *depths, float *conic_opacity, uint32_t *tiles_touched,
                      uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib, gsr_stream_t stream_)

@@ -269,6 +269,146 @@ __global__ void __launch_bounds__(256) depth_l1_backward_kernel(int n, float inv
 	dd[base + i] = __ldg(upstream) * (sg * sc * inv_total + mv * (l0 * (yv - 2.f * dv * x0 - x1) - l1 * x0));
 }
 
+
+// ---- multi-scale gradient-matching loss on the aligned depth (train.py:232-251 `gradient_loss`, called at train.py:556-560 and
+// :571-574 on `aligned_depth[:, ::step, ::step]` for step = 1, 2, 4, 8) --------------------------------------------------------
+//   e_p      = m_p (A_p - y_p),  A_p = abs(s) d_p + t  (or A = the prediction itself when no fit is given)
+//   loss_s   = mean_b( [ sum_{p,q horizontal / vertical neighbours on the stride-2^s grid} |e_q - e_p| m_p m_q ] / M_{b,s} ),
+//   M_{b,s}  = sum of the mask on that grid (not divided when M = 0: reduction_image_based, train.py:221-230)
+// The reference slices, multiplies and reduces ~25 eager kernels per scale (x4 scales, twice that in the backward).  Here one
+// kernel visits every full-resolution pixel once and serves all scales whose grid contains it; per (image, scale) it leaves
+// {sum, M, S1 = d(sum)/d(abs s), S0 = d(sum)/dt} in fp64 so the backward can carry the gradient through the closed-form fit.
+constexpr int kGradMaxScales = 4;
+
+struct GradPix { float e, m, d; };
+
+__device__ __forceinline__ GradPix grad_pix(const float *__restrict__ d, const float *__restrict__ y, const float *__restrict__ m,
+                                            size_t i, float sc, float x1)
+{
+	GradPix p;
+	p.d = d[i];
+	p.m = m ? m[i] : 1.f;
+	p.e = p.m * ((sc * p.d + x1) - y[i]);
+	return p;
+}
+__device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); } // torch.abs backward: sign(0) = 0
+
+__global__ void __launch_bounds__(256) depth_grad_forward_kernel(int H, int W, int n_scales, const float *__restrict__ d,
+                                                                 const float *__restrict__ y, const float *__restrict__ m,
+                                                                 const double *__restrict__ fit_sums, double *__restrict__ gstate /*[B][4][4]*/)
+{
+	__shared__ float s_red[8];
+	const int n = H * W;
+	const size_t base = (size_t)blockIdx.y * n;
+	float sc = 1.f, x1 = 0.f;
+	if (fit_sums) {
+		double x0d, x1d, a00, a01, a11, det;
+		solve_scale_shift(fit_sums + blockIdx.y * 5, x0d, x1d, a00, a01, a11, det);
+		sc = fabsf((float)x0d); x1 = (float)x1d;
+	}
+	float acc[kGradMaxScales][4];
+#pragma unroll
+	for (int s = 0; s < kGradMaxScales; s++) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+	for (int k = 0; k < kDepthItems; k++) {
+		const int i = (blockIdx.x * kDepthItems + k) * 256 + threadIdx.x;
+		if (i >= n) continue;
+		const int r = i / W, c = i - r * W;
+		const GradPix p = grad_pix(d, y, m, base + i, sc, x1);
+#pragma unroll
+		for (int s = 0; s < kGradMaxScales; s++) {
+			const int step = 1 << s;
+			if (s >= n_scales || ((r | c) & (step - 1))) continue;
+			acc[s][1] += p.m;
+			if (c + step < W) {
+				const GradPix q = grad_pix(d, y, m, base + i + step, sc, x1);
+				const float dl = q.e - p.e, w = p.m * q.m, sg = sgnf(dl) * w;
+				acc[s][0] += fabsf(dl) * w; acc[s][2] += sg * (q.m * q.d - p.m * p.d); acc[s][3] += sg * (q.m - p.m);
+			}
+			if (r + step < H) {
+				const GradPix q = grad_pix(d, y, m, base + i + (size_t)step * W, sc, x1);
+				const float dl = q.e - p.e, w = p.m * q.m, sg = sgnf(dl) * w;
+				acc[s][0] += fabsf(dl) * w; acc[s][2] += sg * (q.m * q.d - p.m * p.d); acc[s][3] += sg * (q.m - p.m);
+			}
+		}
+	}
+#pragma unroll
+	for (int s = 0; s < kGradMaxScales; s++) {
+		if (s >= n_scales) break;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const double t = block_sum_1d(acc[s][j], s_red);
+			if (threadIdx.x == 0 && t != 0.0) atomicAdd(gstate + ((size_t)blockIdx.y * kGradMaxScales + s) * 4 + j, t);
+		}
+	}
+}
+
+// total[0] = sum_s mean_b( sum_{b,s} / M_{b,s} )
+__global__ void depth_grad_finalize_kernel(int B, int n_scales, const double *__restrict__ gstate, double *__restrict__ total)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	double t = 0.0;
+	for (int b = 0; b < B; b++)
+		for (int s = 0; s < n_scales; s++) {
+			const double *g = gstate + ((size_t)b * kGradMaxScales + s) * 4;
+			t += g[1] != 0.0 ? g[0] / g[1] : g[0];
+		}
+	total[0] = t / (double)B;
+}
+
+__global__ void __launch_bounds__(256) depth_grad_backward_kernel(int H, int W, int n_scales, float inv_B, const float *__restrict__ d,
+                                                                  const float *__restrict__ y, const float *__restrict__ m,
+                                                                  const float *__restrict__ fm, const double *__restrict__ fit_sums,
+                                                                  const double *__restrict__ gstate, const float *__restrict__ upstream,
+                                                                  float *__restrict__ dd, int accumulate)
+{
+	const int n = H * W;
+	const size_t base = (size_t)blockIdx.y * n;
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const float up = __ldg(upstream) * inv_B;
+	float sc = 1.f, x0 = 1.f, x1 = 0.f, l0 = 0.f, l1 = 0.f;
+	float coef[kGradMaxScales];
+	double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+	for (int s = 0; s < kGradMaxScales; s++) {
+		coef[s] = 0.f;
+		if (s >= n_scales) continue;
+		const double *g = gstate + ((size_t)blockIdx.y * kGradMaxScales + s) * 4;
+		const double cf = (double)up / (g[1] != 0.0 ? g[1] : 1.0);
+		coef[s] = (float)cf;
+		g0 += cf * g[2]; g1 += cf * g[3];
+	}
+	if (fit_sums) {
+		double x0d, x1d, a00, a01, a11, det;
+		solve_scale_shift(fit_sums + blockIdx.y * 5, x0d, x1d, a00, a01, a11, det);
+		x0 = (float)x0d; x1 = (float)x1d; sc = fabsf(x0);
+		g0 *= (x0d > 0.0 ? 1.0 : (x0d < 0.0 ? -1.0 : 0.0));   // d abs(s) / ds
+		l0 = det != 0.0 ? (float)((a11 * g0 - a01 * g1) / det) : 0.f;
+		l1 = det != 0.0 ? (float)((-a01 * g0 + a00 * g1) / det) : 0.f;
+	}
+	const int r = i / W, c = i - r * W;
+	const GradPix p = grad_pix(d, y, m, base + i, sc, x1);
+	float g = 0.f;
+#pragma unroll
+	for (int s = 0; s < kGradMaxScales; s++) {
+		const int step = 1 << s;
+		if (s >= n_scales || ((r | c) & (step - 1))) continue;
+		float t = 0.f;
+		if (c + step < W) { const GradPix q = grad_pix(d, y, m, base + i + step, sc, x1); t -= sgnf(q.e - p.e) * q.m; }
+		if (c - step >= 0) { const GradPix q = grad_pix(d, y, m, base + i - step, sc, x1); t += sgnf(p.e - q.e) * q.m; }
+		if (r + step < H) { const GradPix q = grad_pix(d, y, m, base + i + (size_t)step * W, sc, x1); t -= sgnf(q.e - p.e) * q.m; }
+		if (r - step >= 0) { const GradPix q = grad_pix(d, y, m, base + i - (size_t)step * W, sc, x1); t += sgnf(p.e - q.e) * q.m; }
+		g += coef[s] * t;
+	}
+	g *= p.m * p.m;                                        // dL/dA_p: pair weight m_p m_q times de_p/dA_p = m_p
+	float out = g * sc;
+	if (fit_sums) {
+		const float mv = fm ? fm[base + i] : 1.f;
+		out += mv * (l0 * (y[base + i] - 2.f * p.d * x0 - x1) - l1 * x0);
+	}
+	dd[base + i] = accumulate ? dd[base + i] + out : out;
+}
+
 } // namespace
 
 cudaError_t launch_l1_ssim_forward(int planes, int H, int W, const float *taps11, const float *x, const float *y, const float *mask,
@@ -316,6 +456,30 @@ cudaError_t launch_depth_align_l1_backward(int B, int n, const float *d, const f
 {
 	dim3 grid((n + 255) / 256, B);
 	depth_l1_backward_kernel<<<grid, 256, 0, stream>>>(n, 1.0f / ((float)B * (float)n), d, y, fit_mask, loss_mask, sums, aux, upstream, dd);
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_depth_grad_forward(int B, int H, int W, int n_scales, const float *d, const float *y, const float *mask,
+                                      const double *fit_sums, double *gstate, cudaStream_t stream)
+{
+	cudaError_t e;
+	if ((e = cudaMemsetAsync(gstate, 0, (1 + (size_t)B * kGradMaxScales * 4) * sizeof(double), stream)) != cudaSuccess) return e;
+	const int n = H * W;
+	dim3 grid((n + 256 * kDepthItems - 1) / (256 * kDepthItems), B);
+	depth_grad_forward_kernel<<<grid, 256, 0, stream>>>(H, W, n_scales, d, y, mask, fit_sums, gstate + 1);
+	depth_grad_finalize_kernel<<<1, 32, 0, stream>>>(B, n_scales, gstate + 1, gstate);
+	count_launch(3);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_depth_grad_backward(int B, int H, int W, int n_scales, const float *d, const float *y, const float *mask,
+                                       const float *fit_mask, const double *fit_sums, const double *gstate, const float *upstream,
+                                       float *dd, int accumulate, cudaStream_t stream)
+{
+	dim3 grid((H * W + 255) / 256, B);
+	depth_grad_backward_kernel<<<grid, 256, 0, stream>>>(H, W, n_scales, 1.0f / (float)B, d, y, mask, fit_mask, fit_sums, gstate + 1,
+	                                                     upstream, dd, accumulate);
 	count_launch();
 	return cudaGetLastError();
 }

@@ -21,4 +21,13 @@ cudaError_t launch_depth_align_l1_forward(int B, int n, const float *d, const fl
 cudaError_t launch_depth_align_l1_backward(int B, int n, const float *d, const float *y, const float *fit_mask, const float *loss_mask,
                                            const double *sums, const double *aux, const float *upstream, float *dd, cudaStream_t stream);
 
+// Multi-scale gradient-matching loss (train.py:232-251, :556-560, :571-574).  pred / target / mask (NULL = ones) / fit_mask: [B][H][W];
+// fit_sums: fp64[B][5] as written by launch_depth_align_l1_forward (pred is then the raw depth, aligned inside), or NULL (pred is
+// used as is).  gstate: fp64[1 + 16 B]: [0] = sum over scales of the reference's gradient_loss, then {sum, M, S1, S0} per (image, scale).
+cudaError_t launch_depth_grad_forward(int B, int H, int W, int n_scales, const float *d, const float *y, const float *mask,
+                                      const double *fit_sums, double *gstate, cudaStream_t stream);
+cudaError_t launch_depth_grad_backward(int B, int H, int W, int n_scales, const float *d, const float *y, const float *mask,
+                                       const float *fit_mask, const double *fit_sums, const double *gstate, const float *upstream,
+                                       float *dd, int accumulate, cudaStream_t stream);
+
 } // namespace gsr

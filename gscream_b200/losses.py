@@ -4,7 +4,9 @@ utils/loss_utils.py (:27-31, :131-207), SURVEY.md section 8f rank 3.
 Same names, argument order and return values (0-d tensors) as the reference functions, so train.py:535-545 can import them
 from here instead; `l1_ssim(image, gt, mask)` returns both means from ONE forward / ONE backward kernel
 (`gsr_l1_ssim_forward/backward` of include/gsr_b200.h), which is what the train-step loop of bench.py uses;
-`aligned_depth_l1(depth, target, fit_mask, loss_mask)` is the scale/shift-aligned depth L1 of train.py:548-569.
+`aligned_depth_l1(depth, target, fit_mask, loss_mask)` is the scale/shift-aligned depth L1 of train.py:548-569;
+`aligned_depth_losses(...)` adds the four-scale `gradient_loss` of train.py:232-251, :556-560 from the same fit, and
+`gradient_loss` / `multiscale_gradient_loss` are that term alone on an arbitrary prediction.
 Only the rendered image receives a gradient (the target and the mask are data).  No CPU / eager fallback: CPU tensors raise.
 """
 from math import exp
@@ -119,6 +121,98 @@ class _AlignedDepthL1(torch.autograd.Function):
                                                        lm.data_ptr() if lm.numel() else None, state.data_ptr(), up.data_ptr(), grad.data_ptr(),
                                                        torch.cuda.current_stream().cuda_stream))
         return grad.view(shape), None, None, None
+
+
+def _opt_mask(m, name, B, H, W):
+    if m is None:
+        return None
+    mm, Bm, Hm, Wm = _planes(m.to(torch.float32) if m.dtype != torch.float32 else m, name)
+    if (Bm, Hm, Wm) != (B, H, W):
+        raise ValueError("%s must have the shape of the depth map" % name)
+    return mm
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() else None
+
+
+class _AlignedDepthLosses(torch.autograd.Function):
+    """(aligned L1, multi-scale gradient loss) of one rendered depth map from one scale/shift fit.  `align=False`: no fit, the
+    prediction is used as it is and only the gradient term is produced (plain `gradient_loss`)."""
+
+    @staticmethod
+    def forward(ctx, depth, target, fit_mask, l1_mask, grad_mask, n_scales, align):
+        lib = _lib.load()
+        d, B, H, W = _planes(depth, "depth")
+        y, By, Hy, Wy = _planes(target, "target")
+        if (By, Hy, Wy) != (B, H, W):
+            raise ValueError("depth and target shapes differ: %s vs %s" % (tuple(depth.shape), tuple(target.shape)))
+        if not 1 <= int(n_scales) <= 4:
+            raise ValueError("n_scales must be in 1..4 (train.py uses 4)")
+        fm, lm, gm = _opt_mask(fit_mask, "fit_mask", B, H, W), _opt_mask(l1_mask, "l1_mask", B, H, W), _opt_mask(grad_mask, "grad_mask", B, H, W)
+        dev = d.device
+        state = torch.empty(1 + 7 * B, dtype=torch.float64, device=dev) if align else None
+        gstate = torch.empty(1 + 16 * B, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            if align:
+                _lib.check(lib.gsr_depth_align_l1_forward(B, H, W, d.data_ptr(), y.data_ptr(), _ptr(fm), _ptr(lm), state.data_ptr(), stream))
+            _lib.check(lib.gsr_depth_grad_forward(B, H, W, int(n_scales), d.data_ptr(), y.data_ptr(), _ptr(gm),
+                                                  state.data_ptr() if align else None, gstate.data_ptr(), stream))
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(d, y, fm if fm is not None else empty, lm if lm is not None else empty, gm if gm is not None else empty,
+                              state if align else empty, gstate)
+        ctx.dims = (B, H, W, int(n_scales), bool(align), tuple(depth.shape))
+        l1 = (state[0] / float(B * H * W)).to(torch.float32) if align else torch.zeros((), dtype=torch.float32, device=dev)
+        return l1, gstate[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g_l1, g_grad):
+        lib = _lib.load()
+        d, y, fm, lm, gm, state, gstate = ctx.saved_tensors
+        B, H, W, n_scales, align, shape = ctx.dims
+        dev = d.device
+        grad = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        up_g = g_grad.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            if align:
+                up_l = g_l1.to(torch.float32).reshape(1).contiguous()
+                _lib.check(lib.gsr_depth_align_l1_backward(B, H, W, d.data_ptr(), y.data_ptr(), _ptr(fm), _ptr(lm), state.data_ptr(),
+                                                           up_l.data_ptr(), grad.data_ptr(), stream))
+            _lib.check(lib.gsr_depth_grad_backward(B, H, W, n_scales, d.data_ptr(), y.data_ptr(), _ptr(gm), _ptr(fm),
+                                                   state.data_ptr() if align else None, gstate.data_ptr(), up_g.data_ptr(), grad.data_ptr(),
+                                                   1 if align else 0, stream))
+        return grad.view(shape), None, None, None, None, None, None
+
+
+def aligned_depth_losses(depth, target, fit_mask=None, l1_mask=None, grad_mask=None, n_scales=4):
+    """The whole depth branch of train.py:546-560 (reference view) / :563-574 (other views) in one node:
+
+        scale, shift = compute_scale_and_shift(depth, target, fit_mask); scale = torch.abs(scale)
+        aligned = scale * depth + shift
+        l1   = l1_loss(aligned, target)  (l1_mask None)  or  l1_loss_masked(aligned, target, l1_mask)
+        grad = sum(gradient_loss(aligned[:, ::2**s, ::2**s], target[:, ::2**s, ::2**s], grad_mask[:, ::2**s, ::2**s]) for s in range(n_scales))
+
+    Returns (l1, grad); the caller weights them (`refer_depth_lr * l1 + 0.5 * refer_depth_lr_smooth * grad`).  grad_mask None = ones
+    (train.py:560 passes torch.ones_like(gt_mask)).  The gradient w.r.t. `depth` flows through the closed-form fit for both terms."""
+    if target.requires_grad:
+        raise NotImplementedError("fused aligned_depth_losses differentiates w.r.t. the rendered depth only")
+    return _AlignedDepthLosses.apply(depth, target, fit_mask, l1_mask, grad_mask, n_scales, True)
+
+
+def multiscale_gradient_loss(prediction, target, mask=None, n_scales=4):
+    """sum over s < n_scales of gradient_loss(prediction[:, ::2**s, ::2**s], ...) for an arbitrary prediction (no alignment)."""
+    if target.requires_grad:
+        raise NotImplementedError("fused gradient_loss differentiates w.r.t. the prediction only")
+    return _AlignedDepthLosses.apply(prediction, target, None, None, mask, n_scales, False)[1]
+
+
+def gradient_loss(prediction, target, mask):
+    """train.py:232-251 (with its default reduction_image_based): same arguments, same value; strided views
+    (`aligned_depth[:, ::step, ::step]`) are made contiguous first — use aligned_depth_losses / multiscale_gradient_loss to
+    get all four scales from one pass."""
+    return multiscale_gradient_loss(prediction, target, mask, n_scales=1)
 
 
 def aligned_depth_l1(depth, target, fit_mask=None, loss_mask=None):

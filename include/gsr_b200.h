@@ -242,6 +242,26 @@ GSR_API int gsr_depth_align_l1_backward(
     const double *state, const float *upstream, float *grad_depth, gsr_stream_t stream);
 
 /*
+ * Multi-scale gradient-matching depth loss — replaces the loop of train.py:556-560 / :571-574:
+ *     for scale in range(4): loss += w * gradient_loss(aligned[:, ::2^scale, ::2^scale], target[...], mask[...])
+ * with gradient_loss / reduction_image_based of train.py:221-251 (sum of |horizontal| + |vertical| first differences of
+ * mask * (prediction - target), pair-masked, divided by the mask sum of the sub-sampled grid, mean over the batch).
+ *   prediction, target, mask (NULL = ones): [batch, H, W]; n_scales in 1..4 (strides 1, 2, 4, 8).
+ *   fit_state: NULL -> `prediction` is used as it is (plain gradient_loss, gradient w.r.t. prediction);
+ *              else the `state` written by gsr_depth_align_l1_forward for the same depth / target / fit_mask: `prediction` is
+ *              the raw rendered depth, aligned inside as abs(s) * depth + t, and the backward carries the gradient through the fit.
+ *   gstate: DEVICE fp64[1 + 16 * batch]: [0] = the summed loss, then {sum, M, d sum / d abs(s), d sum / d t} per (image, scale).
+ * backward: upstream = DEVICE fp32 scalar dL/d(summed loss); grad [batch, H, W] is overwritten (accumulate = 0) or added to.
+ */
+GSR_API int gsr_depth_grad_forward(
+    int batch, int height, int width, int n_scales, const float *prediction, const float *target, const float *mask,
+    const double *fit_state, double *gstate, gsr_stream_t stream);
+GSR_API int gsr_depth_grad_backward(
+    int batch, int height, int width, int n_scales, const float *prediction, const float *target, const float *mask,
+    const float *fit_mask, const double *fit_state, const double *gstate, const float *upstream, float *grad, int accumulate,
+    gsr_stream_t stream);
+
+/*
  * Introspection for parity tests (device -> device copies out of the private scratch layout).
  * Any output pointer may be NULL.  Shapes: xy[P,2] depths[P] conic_opacity[P,4]
  * tiles_touched[P] point_list[R] ranges[tiles,2] final_T[H*W] n_contrib[H*W].

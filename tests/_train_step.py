@@ -5,6 +5,7 @@ SURVEY.md section 8d "Config 4").  One iteration = what train.py:497-603 does ar
     prefilter_voxel (visible_filter on the anchors)            gaussian_renderer/__init__.py:190-246
     generate_neural_gaussians + rasterize                       gaussian_renderer/__init__.py:104-179
     L1 + (1 - SSIM) on the image, scale/shift-aligned L1 depth  utils/loss_utils.py:27-28,80-110,131-164; train.py:535-560
+    + the four-scale gradient-matching depth loss               train.py:232-251, 556-560
     scaling regulariser, backward, densification statistics,    train.py:575-612, scene/gaussian_model.py:729-757
     Adam step
 
@@ -54,6 +55,16 @@ def compute_scale_and_shift(prediction, target, mask):
     return x_0, x_1
 
 
+def gradient_loss(prediction, target, mask):
+    """train.py:232-251 with reduction_image_based (:221-230): pair-masked L1 of the first differences, per-image mask mean."""
+    M = torch.sum(mask, (1, 2))
+    diff = mask * (prediction - target)
+    grad_x = torch.abs(diff[:, :, 1:] - diff[:, :, :-1]) * (mask[:, :, 1:] * mask[:, :, :-1])
+    grad_y = torch.abs(diff[:, 1:, :] - diff[:, :-1, :]) * (mask[:, 1:, :] * mask[:, :-1, :])
+    image_loss = torch.sum(grad_x, (1, 2)) + torch.sum(grad_y, (1, 2))
+    return torch.mean(torch.where(M != 0, image_loss / torch.where(M != 0, M, torch.ones_like(M)), image_loss))
+
+
 class TrainStep:
     def __init__(self, rast_module, decode_fn, A=100000, k=10, W=1008, H=567, seed=4, device="cuda", fused_losses=False):
         from gscream_b200 import scenes
@@ -92,11 +103,15 @@ class TrainStep:
             l1 = (image - self.target).abs().mean()
             loss = 0.8 * l1 + 0.2 * (1.0 - ssim(image, self.target, self.window))
         if self.fused_losses:
-            loss = loss + 0.1 * losses.aligned_depth_l1(depth, self.target_depth, self.valid)   # gsr_depth_align_l1_*
+            d_l1, d_gl = losses.aligned_depth_losses(depth, self.target_depth, self.valid, None, self.valid)   # gsr_depth_align_l1_* + gsr_depth_grad_*
+            loss = loss + 0.1 * d_l1 + 0.5 * 0.01 * d_gl
         else:
             s, t = compute_scale_and_shift(depth, self.target_depth, self.valid)
             aligned = s.abs().view(-1, 1, 1) * depth + t.view(-1, 1, 1)
             loss = loss + 0.1 * (aligned - self.target_depth).abs().mean()
+            for sc in range(4):                                                 # train.py:556-560
+                step = pow(2, sc)
+                loss = loss + 0.5 * 0.01 * gradient_loss(aligned[:, ::step, ::step], self.target_depth[:, ::step, ::step], self.valid[:, ::step, ::step])
         loss = loss + 0.01 * scaling.prod(dim=1).mean()
         self.opt.zero_grad(set_to_none=True)
         loss.backward()

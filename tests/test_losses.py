@@ -154,3 +154,92 @@ def test_gpu_aligned_depth_l1_train_step_size_vs_fp64():
     l.backward()
     assert abs(float(l) - float(l64)) <= 1e-5 * abs(float(l64))
     _close(x.grad.double().cpu().numpy(), g64.cpu().numpy(), 2e-5, "aligned depth gradient at train-step size")
+
+
+# ---- four-scale gradient-matching loss from the same fit (train.py:232-251, :556-560, :571-574) ------------------------------
+DEPTHGRAD_GOLDEN = ("depthgrad_ref_view", "depthgrad_other_view", "depthgrad_b2_holes", "depthgrad_plain_b2", "depthgrad_tiny",
+                    "depthgrad_one_scale")
+
+
+def _load_depthgrad(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    fit = None if z["fit"].size == 0 else z["fit"]
+    return z, fit, (fit if int(z["masked_l1"]) else None), z["grad_mask"], int(z["n_scales"]), bool(int(z["aligned"]))
+
+
+@pytest.mark.parametrize("name", DEPTHGRAD_GOLDEN)
+def test_fused_depth_loss_closed_forms_match_reference_autograd(golden_dir, name):
+    """CPU: the closed forms the CUDA kernels evaluate (tests/_depthgrad_emul.py), including the hand-derived gradient through
+    the scale/shift fit, against the reference's own functions and autograd in fp64."""
+    import _depthgrad_emul as em
+    z, fit, l1m, gm, n_scales, aligned = _load_depthgrad(golden_dir, name)
+    l1, gl, grad = em.fused_depth_losses(z["depth"], z["target"], fit, l1m, gm, n_scales, aligned, up_l1=0.7, up_gl=1.9)
+    assert abs(gl - float(z["f64.gl"])) <= 1e-9 * max(abs(float(z["f64.gl"])), 1e-12)
+    if aligned:
+        assert abs(l1 - float(z["f64.l1"])) <= 1e-9 * abs(float(z["f64.l1"]))
+    ref = 0.7 * z["f64.g_l1"] + 1.9 * z["f64.g_gl"]
+    _close(grad, ref, 1e-8, "closed-form gradient")
+
+
+@pytest.mark.parametrize("name", ("depthgrad_plain_b2", "depthgrad_tiny", "depthgrad_one_scale"))
+def test_restatement_of_gradient_loss_matches_reference(golden_dir, name):
+    """Pins tests/_train_step.gradient_loss (the eager depth-smoothness term of bench.py's reference arm) to the reference's."""
+    z, fit, l1m, gm, n_scales, aligned = _load_depthgrad(golden_dir, name)
+    assert not aligned
+    d, y, m = torch.from_numpy(z["depth"]).double(), torch.from_numpy(z["target"]).double(), torch.from_numpy(gm).double()
+    per = [float(ts.gradient_loss(d[:, ::2 ** s, ::2 ** s], y[:, ::2 ** s, ::2 ** s], m[:, ::2 ** s, ::2 ** s])) for s in range(n_scales)]
+    np.testing.assert_allclose(per, z["f64.per_scale"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DEPTHGRAD_GOLDEN)
+def test_gpu_depth_gradient_loss_matches_reference_golden(golden_dir, name):
+    from gscream_b200 import losses
+    z, fit, l1m, gm, n_scales, aligned = _load_depthgrad(golden_dir, name)
+    dev = torch.device("cuda")
+    t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+    d = torch.from_numpy(z["depth"]).to(dev).requires_grad_(True)
+    y = t(z["target"])
+    spread = float(np.abs(z["g_gl"] - z["f64.g_gl"]).max()) + float(np.abs(z["g_l1"] - z["f64.g_l1"]).max())
+    if aligned:
+        l1, gl = losses.aligned_depth_losses(d, y, t(fit), t(l1m), t(gm), n_scales=n_scales)
+        assert abs(float(l1) - float(z["f64.l1"])) <= 1e-5 * abs(float(z["f64.l1"]))
+        assert abs(float(gl) - float(z["f64.gl"])) <= 1e-5 * abs(float(z["f64.gl"]))
+        g, = torch.autograd.grad(0.7 * l1 + 1.9 * gl, d)
+        ref = 0.7 * z["f64.g_l1"] + 1.9 * z["f64.g_gl"]
+        _close(g.cpu().numpy().astype(np.float64), ref, 1e-5, "d (l1, grad loss) / d depth", extra=6.0 * spread)
+        # the L1 half alone is the older single-term node
+        d2 = torch.from_numpy(z["depth"]).to(dev).requires_grad_(True)
+        l1b = losses.aligned_depth_l1(d2, y, t(fit), t(l1m))
+        assert abs(float(l1b) - float(l1)) <= 1e-6 * abs(float(l1))
+    else:
+        gl = losses.multiscale_gradient_loss(d, y, t(gm), n_scales=n_scales)
+        assert abs(float(gl) - float(z["f64.gl"])) <= 1e-5 * abs(float(z["f64.gl"]))
+        g, = torch.autograd.grad(1.9 * gl, d)
+        _close(g.cpu().numpy().astype(np.float64), 1.9 * z["f64.g_gl"], 1e-5, "d grad loss / d prediction", extra=6.0 * spread)
+        # the reference's call pattern: one gradient_loss per strided view (train.py:558-560)
+        d3 = torch.from_numpy(z["depth"]).to(dev)
+        per = [float(losses.gradient_loss(d3[:, ::2 ** s, ::2 ** s], y[:, ::2 ** s, ::2 ** s], t(gm)[:, ::2 ** s, ::2 ** s])) for s in range(n_scales)]
+        np.testing.assert_allclose(per, z["f64.per_scale"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_depth_losses_train_step_size_vs_fp64_closed_forms():
+    """567x1008 (the SPIN-NeRF size): CUDA vs the fp64 closed forms pinned above."""
+    import _depthgrad_emul as em
+    from gscream_b200 import losses
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(9)
+    H, W = 567, 1008
+    depth = 2.0 + 8.0 * torch.rand(1, H, W, generator=g)
+    target = (0.8 * depth + 1.0 + 0.5 * torch.randn(1, H, W, generator=g)).clamp(min=0.1)
+    valid = (torch.rand(1, H, W, generator=g) > 0.1).float()
+    l1_64, gl_64, g64 = em.fused_depth_losses(depth.numpy(), target.numpy(), valid.numpy(), valid.numpy(), valid.numpy(), 4, True, 1.0, 0.5)
+    x = depth.to(dev).requires_grad_(True)
+    l1, gl = losses.aligned_depth_losses(x, target.to(dev), valid.to(dev), valid.to(dev), valid.to(dev))
+    (l1 + 0.5 * gl).backward()
+    assert abs(float(l1) - l1_64) <= 1e-5 * abs(l1_64) and abs(float(gl) - gl_64) <= 1e-5 * abs(gl_64)
+    # sign(e_q - e_p) of a near-tie can flip in fp32: allow isolated pixels, bound everything else tightly
+    err = np.abs(x.grad.double().cpu().numpy() - g64)
+    scale = np.abs(g64).max()
+    assert int((err > 2e-5 * scale).sum()) <= 32, int((err > 2e-5 * scale).sum())
