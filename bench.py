@@ -399,7 +399,8 @@ def run_reference(args, cfg, rank, world, local):
 def run_train_step(args, rank, world, local):
     """BASELINE.json configs[3] substitute (SURVEY.md 8d "Config 4"): the train-step-equivalent loop of tests/_train_step.py,
     1 GPU.  `--impl ours`: fused CUDA decode + this repo's rasterizer + fused L1/SSIM and aligned-depth losses + fused statistics; `--impl reference`: torch decode (the reference's
-    generate_neural_gaussians restated) + the reference's own rasterizer build.  Adam is plain torch in both."""
+    generate_neural_gaussians restated) + the reference's own rasterizer build + eager losses + torch.optim.Adam (its own code path).
+    `ours` additionally uses the fused four-scale depth gradient loss and the fused multi-tensor Adam."""
     if rank != 0:
         return None
     import _train_step as ts
@@ -421,10 +422,11 @@ def run_train_step(args, rank, world, local):
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic anchors / target image / target depth (the SPIN-NeRF 'book' scene and train.py's dependencies are absent)",
            "config": {"workload": "config4 substitute: %d anchors x %d offsets, %dx%d, prefilter + decode + rasterize (RGB+depth+uncertainty) + "
-                                  "L1/SSIM/aligned-depth losses + densification statistics + Adam; P = %d Gaussians from %d visible anchors" % (A, k, W, H, loop.last["P"], loop.last["n_vis"]),
+                                  "L1/SSIM/aligned-depth/4-scale depth-gradient losses + densification statistics + Adam; P = %d Gaussians from %d visible anchors" % (A, k, W, H, loop.last["P"], loop.last["n_vis"]),
                       "decode": "fused CUDA (gsr_decode_*)" if args.impl == "ours" else "torch eager (reference code path)",
                       "rasterizer": "libgsr_b200" if args.impl == "ours" else "reference CUDA build (oracle/_ref/dgr3)",
-                      "losses": "fused L1 + SSIM (gsr_l1_ssim_*) and aligned-depth L1 (gsr_depth_align_l1_*); Adam eager" if args.impl == "ours" else "torch eager",
+                      "losses": "fused L1 + SSIM (gsr_l1_ssim_*), aligned-depth L1 (gsr_depth_align_l1_*), 4-scale depth gradient loss (gsr_depth_grad_*)" if args.impl == "ours" else "torch eager",
+                      "optimizer": "fused multi-tensor Adam (gsr_adam_step)" if args.impl == "ours" else "torch.optim.Adam (foreach)",
                       "densification_statistics": "fused (gsr_training_statis)" if args.impl == "ours" else "torch eager (reference method)"},
            "clocks": clocks}
     if args.impl == "reference":

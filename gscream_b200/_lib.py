@@ -44,6 +44,7 @@ PROTOTYPES = {
     "gsr_depth_align_l1_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_depth_grad_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_depth_grad_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "gsr_adam_step": (_i, [_i, _vp, _vp]),
     "gsr_launch_count": (_i64, [_i]),
     "gsr_profile_enable": (_i, [_i]),
     "gsr_profile_read": (_i, [_i, _vp, _i]),

@@ -7,7 +7,10 @@
 #include "gsr_internal.cuh"
 #include "gsr_decode.cuh"
 #include "gsr_loss.cuh"
+#include "gsr_optim.cuh"
 #include <atomic>
+#include <cmath>
+#include <vector>
 
 namespace gsr {
 
@@ -492,6 +495,34 @@ int gsr_depth_grad_backward(int batch, int height, int width, int n_scales, cons
 	StageTimer t(kLossBwd, stream);
 	GSR_CUDA(launch_depth_grad_backward(batch, height, width, n_scales, prediction, target, mask, fit_mask, fit_state ? fit_state + 1 : nullptr,
 	                                    gstate, upstream, grad, accumulate, stream));
+	return 0;
+}
+
+int gsr_adam_step(int n_tensors, const gsr_adam_tensor *tensors_host, gsr_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (n_tensors < 0 || (n_tensors > 0 && !tensors_host)) return GSR_E_BADARG;
+	std::vector<AdamTensor> tab;
+	tab.reserve((size_t)n_tensors);
+	for (int k = 0; k < n_tensors; k++) {
+		const gsr_adam_tensor &a = tensors_host[k];
+		if (a.numel < 0 || a.step < 1) return GSR_E_BADARG;
+		if (a.numel == 0) continue;
+		if (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq) return GSR_E_BADARG;
+		AdamTensor t;
+		t.param = a.param; t.grad = a.grad; t.exp_avg = a.exp_avg; t.exp_avg_sq = a.exp_avg_sq; t.n = a.numel;
+		const double bc1 = 1.0 - std::pow((double)a.beta1, (double)a.step), bc2 = 1.0 - std::pow((double)a.beta2, (double)a.step);
+		t.one_minus_beta1 = (float)(1.0 - (double)a.beta1);
+		t.beta2 = a.beta2;
+		t.one_minus_beta2 = (float)(1.0 - (double)a.beta2);
+		t.eps = a.eps;
+		t.weight_decay = a.weight_decay;
+		t.step_size = (float)((double)a.lr / bc1);
+		t.bias_correction2_sqrt = (float)std::sqrt(bc2);
+		t.pad = 0;
+		tab.push_back(t);
+	}
+	GSR_CUDA(launch_adam_step((int)tab.size(), tab.data(), stream));
 	return 0;
 }
 

@@ -262,6 +262,29 @@ GSR_API int gsr_depth_grad_backward(
     gsr_stream_t stream);
 
 /*
+ * Multi-tensor Adam step (second half) — replaces `gaussians.optimizer.step()` (train.py:611) of the
+ * optimizer built by GaussianModel.training_setup as torch.optim.Adam(l, lr=0.0, eps=1e-15) (scene/gaussian_model.py:374-407):
+ * every tensor of every parameter group in ONE launch (24 tensors per launch), each element read and written once.
+ * Arithmetic and order of operations are torch.optim.Adam's (amsgrad = False, maximize = False):
+ *     g += weight_decay * p;  m += (g - m) (1 - beta1);  v = v beta2 + (1 - beta2) g g;
+ *     p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * with the two bias corrections evaluated in double precision on the host from each tensor's own `step`.
+ *   tensors_host: HOST array of n_tensors descriptors of DEVICE fp32 arrays (contiguous, numel elements each; numel == 0 is
+ *   skipped); `step` is the step count INCLUDING this update (>= 1).  param / exp_avg / exp_avg_sq are updated in place.
+ */
+typedef struct gsr_adam_tensor {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    int64_t numel;
+    int64_t step;
+    float lr, beta1, beta2, eps, weight_decay;
+    int32_t reserved;
+} gsr_adam_tensor;
+GSR_API int gsr_adam_step(int n_tensors, const gsr_adam_tensor *tensors_host, gsr_stream_t stream);
+
+/*
  * Introspection for parity tests (device -> device copies out of the private scratch layout).
  * Any output pointer may be NULL.  Shapes: xy[P,2] depths[P] conic_opacity[P,4]
  * tiles_touched[P] point_list[R] ranges[tiles,2] final_T[H*W] n_contrib[H*W].

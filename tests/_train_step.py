@@ -12,7 +12,8 @@ SURVEY.md section 8d "Config 4").  One iteration = what train.py:497-603 does ar
 on a synthetic anchor model (10^5 anchors x 10 offsets, 1008x567) with synthetic target image / depth.  Both arms run
 this same file; they differ only in `decode` (torch restatement vs gscream_b200.decode) and `rast` (reference build vs
 gscream_b200.rasterizer).  The reference arm's losses are eager torch (its own code path); this repo's arm uses the fused L1 + SSIM and aligned-depth-L1
-kernels (gscream_b200.losses) and the fused densification statistics (gscream_b200.stats); the optimizer is plain torch on both sides.
+and four-scale gradient-loss kernels (gscream_b200.losses), the fused densification statistics (gscream_b200.stats) and the fused Adam
+(gscream_b200.optim); the reference arm's optimizer is torch.optim.Adam, as in the reference.
 """
 import math
 
@@ -79,7 +80,11 @@ class TrainStep:
         self.target_depth = (2.0 + 10.0 * torch.rand(1, H, W, generator=g)).to(self.dev)
         self.valid = torch.ones(1, H, W, device=self.dev)
         self.window = _gaussian_window(device=self.dev)
-        self.opt = torch.optim.Adam(self.pc.parameters(), lr=1e-4, eps=1e-15)
+        if fused_losses:
+            from gscream_b200 import optim
+            self.opt = optim.Adam(self.pc.parameters(), lr=1e-4, eps=1e-15)          # one launch for all tensors (gsr_adam_step)
+        else:
+            self.opt = torch.optim.Adam(self.pc.parameters(), lr=1e-4, eps=1e-15)   # scene/gaussian_model.py:407
         ad.init_statis_buffers(self.pc)
         self.campos = self.cam["campos"].to(self.dev)
         self.settings = ad.make_settings(self.mod, self.cam, self.bg, self.dev)
