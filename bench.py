@@ -435,9 +435,30 @@ def run_train_step(args, rank, world, local):
                                "sample": "full loop, %d steps, reference rasterizer + eager torch decode on the same GPU" % args.steps}
         out["e2e"] = {"value": out["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         return out
-    # ---- decode alone: fused CUDA vs eager torch on the same anchors / visibility (fwd + bwd), device time ----
     from gscream_b200 import _lib
     lib = _lib.load()
+    # ---- where the iteration's GPU time goes: per-stage CUDA-event sums over 10 more iterations (library kernels only) ----
+    names = ("preprocess", "depth_order_scan", "binning", "blend_forward", "blend_backward", "gaussian_backward", "decode_forward",
+             "decode_backward", "losses_forward", "losses_backward", "adam_step")
+    lib.gsr_profile_enable(1)
+    for _ in range(10):
+        loop.step()
+    torch.cuda.synchronize()
+    buf = np.zeros(256, np.float32)
+    stage_ms = {}
+    for sid, name in enumerate(names):
+        n = lib.gsr_profile_read(sid, buf.ctypes.data, 256)
+        stage_ms[name] = float(buf[:n].sum() / 10.0) if n > 0 else None
+    lib.gsr_profile_enable(0)
+    out["stage_ms"] = stage_ms
+    n_param = sum(p_.numel() for p_ in loop.pc.parameters())
+    peak, peak_src = _peaks()
+    if stage_ms["adam_step"]:
+        adam_bytes = 28 * n_param    # read param, grad, exp_avg, exp_avg_sq; write param, exp_avg, exp_avg_sq (fp32)
+        out["optimizer"] = {"kernel": "adam_step_kernel", "parameters": n_param, "kernel_ms": stage_ms["adam_step"],
+                            "roofline": {"bound": "hbm", "algorithmic_bytes": adam_bytes, "achieved": adam_bytes / (stage_ms["adam_step"] * 1e-3) / 1e9,
+                                         "peak": peak, "unit": "GB/s", "frac": adam_bytes / (stage_ms["adam_step"] * 1e-3) / 1e9 / peak, "peak_source": peak_src}}
+    # ---- decode alone: fused CUDA vs eager torch on the same anchors / visibility (fwd + bwd), device time ----
     pc, campos = loop.pc, loop.campos
     with torch.no_grad():
         rast = mod.GaussianRasterizer(raster_settings=loop.settings)
@@ -466,7 +487,6 @@ def run_train_step(args, rank, world, local):
     n_vis, P = loop.last["n_vis"], loop.last["P"]
     fwd_bytes = n_vis * (128 + 12 + 12 * k + 24 + 5 * k) + A + 60 * P
     bwd_bytes = n_vis * (128 + 12 + 12 * k + 24) * 2 + 64 * P + 4 * k * n_vis
-    peak, peak_src = _peaks()
     out["decode"] = {"fused_fwd_bwd_ms": ms_f / 20, "torch_fwd_bwd_ms": ms_t / 20, "kernel_ms": st, "gpu_launches_per_decode": launches / 23.0,
                      "visible_anchors": n_vis, "gaussians": P,
                      "roofline": {"bound": "hbm", "kernel": "decode_backward_kernel", "algorithmic_bytes_fwd": fwd_bytes, "algorithmic_bytes_bwd": bwd_bytes,

@@ -23,7 +23,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // When enabled, every stage launch is bracketed by a cudaEvent pair on the caller's stream (a ring of
 // kProfCap pairs per stage).  Nothing is synchronised here; gsr_profile_read() is called after the
 // caller's own synchronise.  Disabled (the default) it costs one branch per stage.
-enum Stage { kPre = 0, kDepthScan, kBin, kBlendFwd, kBlendBwd, kPreBwd, kDecodeFwd, kDecodeBwd, kLossFwd, kLossBwd, kNumStages };
+enum Stage { kPre = 0, kDepthScan, kBin, kBlendFwd, kBlendBwd, kPreBwd, kDecodeFwd, kDecodeBwd, kLossFwd, kLossBwd, kOptim, kNumStages };
 static constexpr int kProfCap = 256;
 static bool g_prof_on = false;
 static cudaEvent_t g_ev[kNumStages][kProfCap][2];
@@ -511,17 +511,18 @@ int gsr_adam_step(int n_tensors, const gsr_adam_tensor *tensors_host, gsr_stream
 		if (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq) return GSR_E_BADARG;
 		AdamTensor t;
 		t.param = a.param; t.grad = a.grad; t.exp_avg = a.exp_avg; t.exp_avg_sq = a.exp_avg_sq; t.n = a.numel;
-		const double bc1 = 1.0 - std::pow((double)a.beta1, (double)a.step), bc2 = 1.0 - std::pow((double)a.beta2, (double)a.step);
-		t.one_minus_beta1 = (float)(1.0 - (double)a.beta1);
-		t.beta2 = a.beta2;
-		t.one_minus_beta2 = (float)(1.0 - (double)a.beta2);
-		t.eps = a.eps;
-		t.weight_decay = a.weight_decay;
-		t.step_size = (float)((double)a.lr / bc1);
+		const double bc1 = 1.0 - std::pow(a.beta1, (double)a.step), bc2 = 1.0 - std::pow(a.beta2, (double)a.step);
+		t.one_minus_beta1 = (float)(1.0 - a.beta1);
+		t.beta2 = (float)a.beta2;
+		t.one_minus_beta2 = (float)(1.0 - a.beta2);
+		t.eps = (float)a.eps;
+		t.weight_decay = (float)a.weight_decay;
+		t.step_size = (float)(a.lr / bc1);
 		t.bias_correction2_sqrt = (float)std::sqrt(bc2);
 		t.pad = 0;
 		tab.push_back(t);
 	}
+	StageTimer timer(kOptim, stream);
 	GSR_CUDA(launch_adam_step((int)tab.size(), tab.data(), stream));
 	return 0;
 }

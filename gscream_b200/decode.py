@@ -39,6 +39,16 @@ def _f32c(t, name):
     return t.contiguous()
 
 
+def _zeros_like_many(tensors):
+    """Zero-filled fp32 tensors shaped like `tensors`, as contiguous views (256-B aligned) of one flat zero-filled buffer."""
+    offsets, total = [], 0
+    for t in tensors:
+        offsets.append(total)
+        total += (t.numel() + 63) // 64 * 64
+    flat = torch.zeros(max(total, 1), dtype=torch.float32, device=tensors[0].device)
+    return [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offsets, tensors)]
+
+
 class _DecodeAnchors(torch.autograd.Function):
     """inputs: anchor[A,3] feat[A,32] offset[A,k,3] scaling[A,6] campos[3] visible_mask (bool[A] or None) + the 16 MLP
     tensors ({opacity, uncertainty, cov, colour} x {w1, b1, w2, b2}).
@@ -110,11 +120,8 @@ class _DecodeAnchors(torch.autograd.Function):
             return None if g is None else g.to(torch.float32).contiguous()
 
         ups = [up(g) for g in (d_xyz, d_color, d_opacity, d_uncertainty, d_scaling, d_rot, d_nop)]
-        g_anchor = torch.zeros_like(anchor)
-        g_feat = torch.zeros_like(feat)
-        g_offset = torch.zeros_like(offset)
-        g_scaling = torch.zeros_like(scaling)
-        g_mlp = [torch.zeros_like(t) for t in mlp]
+        # twenty zero-filled outputs carved out of ONE zero-filled allocation (one fill launch instead of twenty)
+        g_anchor, g_feat, g_offset, g_scaling, *g_mlp = _zeros_like_many((anchor, feat, offset, scaling) + tuple(mlp))
         with torch.cuda.device(dev):
             _lib.check(lib.gsr_decode_backward(A, feat_dim, k, n_vis, P, anchor.data_ptr(), feat.data_ptr(), offset.data_ptr(),
                                                scaling.data_ptr(), campos.data_ptr(), _ptr_array(mlp), scratch.data_ptr(), scratch.numel(),

@@ -19,8 +19,8 @@ class _AdamTensor(ctypes.Structure):
     """gsr_adam_tensor of include/gsr_b200.h."""
     _fields_ = [("param", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("exp_avg", ctypes.c_void_p), ("exp_avg_sq", ctypes.c_void_p),
                 ("numel", ctypes.c_int64), ("step", ctypes.c_int64),
-                ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
-                ("weight_decay", ctypes.c_float), ("reserved", ctypes.c_int32)]
+                ("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double),
+                ("weight_decay", ctypes.c_double)]
 
 
 class Adam(torch.optim.Optimizer):
@@ -79,7 +79,7 @@ class Adam(torch.optim.Optimizer):
                 per_device.setdefault(p.device, []).append(
                     _AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
                                 int(round(float(st["step"]))), float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
-                                float(group["weight_decay"]), 0))
+                                float(group["weight_decay"])))
         lib = _lib.load() if per_device else None
         for dev, rows in per_device.items():
             table = (_AdamTensor * len(rows))(*rows)

@@ -279,8 +279,7 @@ typedef struct gsr_adam_tensor {
     float *exp_avg_sq;
     int64_t numel;
     int64_t step;
-    float lr, beta1, beta2, eps, weight_decay;
-    int32_t reserved;
+    double lr, beta1, beta2, eps, weight_decay;   /* doubles: torch evaluates 1 - beta and lr / (1 - beta^step) in Python floats */
 } gsr_adam_tensor;
 GSR_API int gsr_adam_step(int n_tensors, const gsr_adam_tensor *tensors_host, gsr_stream_t stream);
 
@@ -310,7 +309,7 @@ GSR_API int gsr_debug_plain_point_list(int on);
  * elapsed milliseconds of the recorded launches of one stage to HOST memory and returns how many there were.
  * Stages: 0 preprocess, 1 depth order + scan, 2 instance binning, 3 blend forward, 4 blend backward,
  * 5 per-Gaussian backward, 6 decode forward (stages 1 + 2), 7 decode backward,
- * 8 L1+SSIM forward, 9 L1+SSIM backward.
+ * 8 image / depth losses forward, 9 image / depth losses backward, 10 Adam step.
  */
 GSR_API int gsr_profile_enable(int on);
 GSR_API int gsr_profile_read(int stage, float *ms_host, int capacity);

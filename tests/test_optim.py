@@ -96,10 +96,11 @@ def test_descriptor_struct_matches_header():
     from gscream_b200 import optim
     hdr = open(os.path.join(HERE, "..", "include", "gsr_b200.h")).read()
     body = re.search(r"typedef struct gsr_adam_tensor \{(.*?)\} gsr_adam_tensor;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = [n.strip(" *") for decl in body.split(";") if decl.strip() for n in decl.split(",")]
     names = [n.split()[-1].lstrip("*") for n in names]
     assert names == [f[0] for f in optim._AdamTensor._fields_]
-    assert ctypes.sizeof(optim._AdamTensor) == 72 and optim._AdamTensor.numel.offset == 32 and optim._AdamTensor.lr.offset == 48
+    assert ctypes.sizeof(optim._AdamTensor) == 88 and optim._AdamTensor.numel.offset == 32 and optim._AdamTensor.lr.offset == 48
 
 
 def _kernel_order_numpy(p, g, m, v, lr, beta1, beta2, eps, wd, step):
