@@ -55,14 +55,23 @@ def _check_ints_and_projection(m, e, ref_radii, ref_geom, ref_img, ref_plist, R)
     assert np.array_equal(e["final_T"].view(np.uint32), ref_img["final_T"].view(np.uint32))  # same alpha chain, bit for bit
 
 
-def _check_floats(m, ref, spread=None):
+def _check_floats(m, ref, spread=None, truth=None):
+    """`truth` (optional, fp64 oracle gradients): arbiter for ill-conditioned cases where the reference's own atomic-order
+    jitter is of the order of the tolerance and two or four of its runs under-estimate it — a tensor that misses the
+    reference by more than the tolerance still passes if it is at least as close to the fp64 result as the reference is."""
     for k in ("color", "depth", "uncertainty"):
         tol = REL * np.abs(ref[k]).max()
         assert np.abs(m[k] - ref[k]).max() <= tol, (k, float(np.abs(m[k] - ref[k]).max()), float(tol))
     for k in GRAD_KEYS:
         rel = REL if k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_duncertainty") else 3 * REL
         tol = rel * np.abs(ref[k]).max() + (8.0 * spread[k] if spread else 0.0)
-        assert np.abs(m[k] - ref[k]).max() <= tol, (k, float(np.abs(m[k] - ref[k]).max()), float(tol))
+        err = float(np.abs(m[k] - ref[k]).max())
+        if err > tol and truth is not None and k in truth:
+            t = truth[k].reshape(ref[k].shape)
+            ours_off, ref_off = float(np.abs(m[k] - t).max()), float(np.abs(ref[k] - t).max())
+            assert ours_off <= ref_off + rel * np.abs(ref[k]).max(), (k, "vs fp64 oracle: ours %.3e, reference %.3e" % (ours_off, ref_off), err, float(tol))
+        else:
+            assert err <= tol, (k, err, float(tol))
         assert not m[k][ref["radii"] == 0].any()  # culled Gaussians: exactly zero
 
 
@@ -317,11 +326,11 @@ def test_full_size_against_reference_build(cfg, smult):
     _check_floats(m, r, spread)
 
 
-def _compare_with_reference_build(scene, cam, grads, C):
+def _compare_with_reference_build(scene, cam, grads, C, ref_runs=2, oracle_arbiter=False):
     ref_mod = ru.load_ref(C)
     P, W, H = scene["means3D"].shape[0], cam["W"], cam["H"]
     r = ru.run_impl(ref_mod, scene, cam, grads)
-    r2 = ru.run_impl(ref_mod, scene, cam, grads)
+    reruns = [ru.run_impl(ref_mod, scene, cam, grads) for _ in range(ref_runs - 1)]
     m = ru.run_impl(ours, scene, cam, grads)
     R = r["num_rendered"]
     geom = ru.parse_ref_geom(r["_geom"].cpu().numpy(), P)
@@ -329,8 +338,9 @@ def _compare_with_reference_build(scene, cam, grads, C):
     binn = ru.parse_ref_binning(r["_binning"].cpu().numpy(), R)
     e = _export(m, P, W, H)
     _check_ints_and_projection(m, e, r["radii"], geom, img, binn["point_list"], R)
-    spread = {k: float(np.abs(r2[k] - r[k]).max()) for k in GRAD_KEYS}
-    _check_floats(m, r, spread)
+    spread = {k: max(float(np.abs(r2[k] - r[k]).max()) for r2 in reruns) for k in GRAD_KEYS}
+    truth = _oracle_run(scene, cam, grads, "f64")[1] if oracle_arbiter else None
+    _check_floats(m, r, spread, truth)
     return r
 
 
@@ -351,7 +361,10 @@ def test_adversarial_parameters_against_reference_build(C):
     sc["means3D"][: P // 10, :2] *= 3.0  # far outside the frustum sideways (no x/y frustum test upstream, auxiliary.h:154)
     cam = scenes.make_camera(W, H, yaw_deg=3.0)
     grads = scenes.make_upstream_grads(C, W, H, 900 + C)
-    _compare_with_reference_build(sc, cam, grads, C)
+    # needle splats make the cov2D -> cov3D -> scale / rotation chain ill-conditioned: the reference's dL_dscales moves by up to
+    # 7e-5 (of 9e-2) between its own runs and sits 6e-5 from the fp64 result (ours: 9e-6 and 3e-5; tests/_adv_probe.py), so
+    # its jitter is estimated from four runs and the fp64 oracle arbitrates what still misses
+    _compare_with_reference_build(sc, cam, grads, C, ref_runs=4, oracle_arbiter=True)
 
 
 def test_three_digit_passes_of_the_tile_sort():
