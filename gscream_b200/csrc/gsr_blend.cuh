@@ -190,6 +190,35 @@ struct WarpFeed {
 	}
 };
 
+// Packed FP32 (sm_100: fma.rn.f32x2, SASS FFMA2): one instruction performs two independent IEEE round-to-nearest FMAs on the
+// halves of 64-bit register pairs, so the per-channel accumulations of the blend kernels (the same FMAs, bit for bit) take half the
+// instructions (forward 34 -> 17, backward 64 -> 32 per contributing pair).  Measured on B200 (profiles/r1_ffma2_ab.md): parity-green
+// and SLOWER — forward 0.874 -> 0.889 ms at 72 registers (0.963 ms at 64 registers, where the pair alignment forces spills and
+// ~20 register moves per entry), backward 2.147 -> 2.247 ms with 13 % fewer instructions: an FFMA2 occupies the FMA pipe like the two
+// FFMAs it replaces and has the longer dependent-issue latency, which is what the backward is bound by.  Kept behind the switch.
+#ifndef GSR_FFMA2
+#define GSR_FFMA2 0
+#endif
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+	uint64_t r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+	uint64_t d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+	uint64_t d;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+
 // power = -0.5 (a dx^2 + c dy^2) - b dx dy, CR/forward.cu:524 / CR/backward.cu:524, with the rounding
 // sequence of the reference build's SASS (same in renderCUDA forward and backward, C = 3 and 32):
 //   s = fma(dx, a*dx, (c*dy)*dy) ; power = fma(s, -0.5, -((b*dx)*dy))

@@ -195,6 +195,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 		}
 	}
 
+	// packed copies (GSR_FFMA2, C == 32): the gradient row and column as register pairs for fma.rn.f32x2
+	constexpr bool kPacked = (GSR_FFMA2 != 0) && kLaneChannel && !kGcolSmem;
+	constexpr int kPairs = kPacked ? C / 2 : 1;
+	uint64_t g2[kPairs], gcol2[kPairs];
+	if (kPacked) {
+#pragma unroll
+		for (int i = 0; i < kPairs; i++) {
+			g2[i] = pack2(g[(2 * i) % C], g[(2 * i + 1) % C]);
+			gcol2[i] = pack2(gcol[(2 * i) % (kPacked ? 32 : 1)], gcol[(2 * i + 1) % (kPacked ? 32 : 1)]);
+		}
+	}
+
 	float T = T_final;
 	float X = 0.f, last_alpha = 0.f, last_dot = 0.f;
 	const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
@@ -265,6 +277,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 					if (C > 0) d2 += r2.z * g[0];
 					if (C > 1) d3 += r2.w * g[1 % C];
 					if (C > 2) d0 += cb * g[2 % C];
+				} else if (kPacked) {
+					// two chains of packed FMAs (even / odd 16-B parts), four partial sums folded at the end
+					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
+					uint64_t da = pack2(d0, 0.f), db = 0ull;
+#pragma unroll
+					for (int q = 0; q < C / 4; q++) {
+						const float4 f = f4[q];
+						da = fma2(pack2(f.x, f.y), g2[(2 * q) % kPairs], da);
+						db = fma2(pack2(f.z, f.w), g2[(2 * q + 1) % kPairs], db);
+					}
+					float lo, hi;
+					unpack2(add2(da, db), lo, hi);
+					d0 = lo + hi;
 				} else {
 					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
 #pragma unroll
@@ -329,6 +354,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 				float &s1 = s0, &s2 = s0, &s3 = s0;
 #endif
 				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[lwarp]);
+				if (kPacked) {
+					uint64_t sa = 0ull, sb = 0ull;
+#pragma unroll
+					for (int q = 0; q < 8; q++) {
+						const float4 ww = w4[q];
+						sa = fma2(pack2(ww.x, ww.y), gcol2[(2 * q) % kPairs], sa);
+						sb = fma2(pack2(ww.z, ww.w), gcol2[(2 * q + 1) % kPairs], sb);
+					}
+					float lo, hi;
+					unpack2(add2(sa, sb), lo, hi);
+					red_add(dL_dcolors + (size_t)id * C + lane, lo + hi); // 32 lanes -> one coalesced 128-B RED
+					__syncwarp();
+					continue;
+				}
 				const float4 *c4 = reinterpret_cast<const float4 *>(s_gc + lane * kGcolStride);
 #pragma unroll
 				for (int q = 0; q < 8; q++) {

@@ -42,8 +42,16 @@ constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 #ifndef GSR_FWD_MINBLOCKS
 #define GSR_FWD_MINBLOCKS 4
 #endif
+// keep the per-entry loop rolled (ptxas unrolls it by two, which costs registers): A/B switch
+#ifndef GSR_FWD_UNROLL1
+#define GSR_FWD_UNROLL1 0
+#endif
+// resident CTAs per SM asked of ptxas (register budget = 65536 / (threads x CTAs)); -DGSR_FWD_MINCTAS=n overrides for A/B
+#ifndef GSR_FWD_MINCTAS
+#define GSR_FWD_MINCTAS (GSR_FWD_MINBLOCKS * kCtasPerTile)
+#endif
 template <int C>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPerTile) blend_forward_kernel(
+__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINCTAS) blend_forward_kernel(
     const uint2 *__restrict__ ranges, uint32_t *point_list, int packed, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
@@ -69,6 +77,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 #pragma unroll
 	for (int ch = 0; ch < C; ch++) acc[ch] = 0.f;
 	float D = 0.f, UNC = 0.f;
+	// packed accumulators (GSR_FFMA2, C > 3): channel pairs (2i, 2i+1) and (depth, uncertainty)
+	constexpr bool kPacked = (GSR_FFMA2 != 0) && !TR::kFeatInRec;
+	constexpr int kPairs = kPacked ? C / 2 : 1;
+	uint64_t acc2[kPairs], du2 = 0ull;
+#pragma unroll
+	for (int i = 0; i < kPairs; i++) acc2[i] = 0ull;
 	bool done = !inside;
 
 	if (!__all_sync(0xffffffffu, done)) {
@@ -87,6 +101,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 			uint32_t blended = 0; // bit e: this pixel blended entry e of the chunk
 #if GSR_FWD_EBIT
 			uint32_t ebit = 1u;
+#if GSR_FWD_UNROLL1
+#pragma unroll 1
+#endif
 			for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats, ebit <<= 1) {
 #else
 			for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats) {
@@ -110,6 +127,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 					if (C > 0) acc[0] += r2.z * w;
 					if (C > 1) acc[1 % C] += r2.w * w;
 					if (C > 2) acc[2 % C] += cb * w;
+				} else if (kPacked) {
+					const uint64_t ww = pack2(w, w);
+					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
+#pragma unroll
+					for (int q = 0; q < C / 4; q++) {
+						const float4 f = f4[q];
+						acc2[(2 * q) % kPairs] = fma2(pack2(f.x, f.y), ww, acc2[(2 * q) % kPairs]);
+						acc2[(2 * q + 1) % kPairs] = fma2(pack2(f.z, f.w), ww, acc2[(2 * q + 1) % kPairs]);
+					}
+					du2 = fma2(pack2(r1.z, r1.w), ww, du2);
 				} else {
 					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
 #pragma unroll
@@ -121,8 +148,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 						acc[4 * q + 3] += f.w * w;
 					}
 				}
-				D += r1.z * w;
-				UNC += r1.w * w;
+				if (!kPacked) {
+					D += r1.z * w;
+					UNC += r1.w * w;
+				}
 				T = test_T;
 				last_ring = feed.done + e + 1u;
 #if GSR_FWD_EBIT
@@ -148,6 +177,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINBLOCKS * kCtasPe
 		feed.drain(chunk, m_cur); // nothing may be in flight into shared memory when the warp retires
 	}
 
+	if (kPacked) {
+#pragma unroll
+		for (int i = 0; i < (kPacked ? C / 2 : 0); i++) unpack2(acc2[i], acc[(2 * i) % C], acc[(2 * i + 1) % C]);
+		unpack2(du2, D, UNC);
+	}
 	if (inside) {
 		const size_t pix_id = (size_t)W * py + px;
 		final_T[pix_id] = T;
