@@ -52,13 +52,7 @@
 #ifndef GSR_BWD_PB2
 #define GSR_BWD_PB2 1
 #endif
-// C = 32: store the weights to shared memory before the butterfly, so that its shuffle chain and the colour sums can overlap
-#ifndef GSR_BWD_EARLY_W
-#define GSR_BWD_EARLY_W 0
-#endif
-#if GSR_BWD_EARLY_W && GSR_FFMA2
-#error "GSR_BWD_EARLY_W is written for the scalar colour sums"
-#endif
+
 
 namespace gsr {
 
@@ -342,91 +336,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 			}
 			const uint32_t id = feed.q_id[slot];
 
-#if GSR_BWD_EARLY_W == 2
-			// hand-interleaved: each level of the butterfly (a shuffle round trip of ~25 cycles) is issued, two 16-B parts of the
-			// colour sums (LDS.128 + 4 FMA each) run while it is in flight, then the level's adds
-			if constexpr (kLaneChannel && !kGcolSmem) {
-				s_w[lwarp][lane] = w;
-				__syncwarp();
-				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[lwarp]);
-				float s0 = 0.f, s1 = 0.f;
-#define GSR_COL(q)                                                        \
-	{                                                                     \
-		const float4 ww = w4[q];                                          \
-		s0 += ww.x * gcol[(4 * (q) + 0) % (kGcolSmem ? 1 : 32)];          \
-		s1 += ww.y * gcol[(4 * (q) + 1) % (kGcolSmem ? 1 : 32)];          \
-		s0 += ww.z * gcol[(4 * (q) + 2) % (kGcolSmem ? 1 : 32)];          \
-		s1 += ww.w * gcol[(4 * (q) + 3) % (kGcolSmem ? 1 : 32)];          \
-	}
-				{
-					const bool upper = (lane & 16) != 0;
-					float t[4], keep[4];
-#pragma unroll
-					for (int i = 0; i < 4; i++) {
-						keep[i] = upper ? v[i + 4] : v[i];
-						t[i] = __shfl_xor_sync(0xffffffffu, upper ? v[i] : v[i + 4], 16);
-					}
-					GSR_COL(0) GSR_COL(1)
-#pragma unroll
-					for (int i = 0; i < 4; i++) v[i] = keep[i] + t[i];
-				}
-				{
-					const bool upper = (lane & 8) != 0;
-					float t[2], keep[2];
-#pragma unroll
-					for (int i = 0; i < 2; i++) {
-						keep[i] = upper ? v[i + 2] : v[i];
-						t[i] = __shfl_xor_sync(0xffffffffu, upper ? v[i] : v[i + 2], 8);
-					}
-					GSR_COL(2) GSR_COL(3)
-#pragma unroll
-					for (int i = 0; i < 2; i++) v[i] = keep[i] + t[i];
-				}
-				{
-					const bool upper = (lane & 4) != 0;
-					const float keep = upper ? v[1] : v[0];
-					const float t = __shfl_xor_sync(0xffffffffu, upper ? v[0] : v[1], 4);
-					GSR_COL(4) GSR_COL(5)
-					v[0] = keep + t;
-				}
-				{
-					const float t = __shfl_xor_sync(0xffffffffu, v[0], 2);
-					GSR_COL(6)
-					v[0] += t;
-				}
-				{
-					const float t = __shfl_xor_sync(0xffffffffu, v[0], 1);
-					GSR_COL(7)
-					v[0] += t;
-				}
-#undef GSR_COL
-				red_add(dL_dcolors + (size_t)id * C + lane, s0 + s1); // 32 lanes -> one coalesced 128-B RED
-				if (vowner<NV>(lane)) red_add(gacc + (size_t)id * 8 + vidx<NV>(lane), v[0]);
-				__syncwarp();
-				continue;
-			}
-#endif
-#if GSR_BWD_EARLY_W
-			// publish the weights BEFORE the butterfly: the 9 dependent shuffles below and the colour sums further down (LDS + FMA)
-			// are independent instruction streams, with the barrier out of the way ptxas can interleave them
-			if (kLaneChannel) {
-				s_w[lwarp][lane] = w;
-				__syncwarp();
-			}
-#endif
+			// The butterfly's 9 dependent shuffles and the colour sums below are independent, but ptxas keeps them apart whatever the
+			// source order (weights stored first, hand-interleaved levels, butterfly deferred into the next entry's geometry block:
+			// measured 2.158 / 2.158 / 2.476 ms against 2.148 ms, profiles/r1_bwd_order_ab.md; code at commit 63eca77).
 			warp_transpose_reduce<NV>(v, lane);
-#if !GSR_BWD_EARLY_W
 			if (vowner<NV>(lane)) {
 				const int q = vidx<NV>(lane);
 				if (q < 8) red_add(gacc + (size_t)id * 8 + q, v[0]);
 				else if (q < 8 + C) red_add(dL_dcolors + (size_t)id * C + (q - 8), v[0]);
 			}
-#endif
 			if (kLaneChannel) {
-#if !GSR_BWD_EARLY_W
 				s_w[lwarp][lane] = w;
 				__syncwarp();
-#endif
 #if GSR_BWD_ACC4
 				float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #elif GSR_BWD_PB2
@@ -475,18 +396,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 #else
 				red_add(dL_dcolors + (size_t)id * C + lane, s0);
 #endif
-#if GSR_BWD_EARLY_W
-				if (vowner<NV>(lane)) red_add(gacc + (size_t)id * 8 + vidx<NV>(lane), v[0]);
-#endif
 				__syncwarp();
 			}
-#if GSR_BWD_EARLY_W
-			else if (vowner<NV>(lane)) {
-				const int q = vidx<NV>(lane);
-				if (q < 8) red_add(gacc + (size_t)id * 8 + q, v[0]);
-				else if (q < 8 + C) red_add(dL_dcolors + (size_t)id * C + (q - 8), v[0]);
-			}
-#endif
 		}
 		feed.done += m_cur;
 		__syncwarp(); // the stage buffer and the ring slots of this chunk may be reused
@@ -494,204 +405,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 	}
 	feed.drain(chunk, 0);
 }
-
-// ---- C = 32 variant with the scalar-sum butterfly deferred by one entry (-DGSR_BWD_DEFER=1) ---------------------------------
-// The shipped loop runs, per contributing (warp, Gaussian) pair, geometry -> dot product -> recurrence -> the 8 scalar terms ->
-// a 5-level transpose-reduce butterfly (9 dependent SHFL, ~25 cycles each) -> RED, then the colour sums.  ncu shows the kernel
-// waiting on exactly such chains (63 % issue utilisation, `wait` + `short_scoreboard` stalls at 4 warps per scheduler), and ptxas
-// will not overlap the butterfly with the colour sums (it hoists the FMAs and leaves the shuffle chain at the end of the block,
-// however the source is ordered).  Here the 8 terms of entry e are kept in registers and reduced at the top of entry e+1's
-// iteration, in the basic block that also loads and evaluates entry e+1's Gaussian (LDS, power, exp, alpha) — independent work the
-// scheduler interleaves with the shuffle chain; the colour sums move ahead of the dot product (they only need w = alpha * T), so
-// the carried terms cross no high-pressure region.  Same values, same atomics; only the issue order changes.
-#ifndef GSR_BWD_DEFER
-#define GSR_BWD_DEFER 0
-#endif
-#if GSR_BWD_DEFER
-__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(32)) blend_backward_defer_kernel(
-    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
-    const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
-    const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
-    const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dpixel_uncs,
-    float *__restrict__ gacc, float *__restrict__ dL_dcolors)
-{
-	constexpr int C = 32;
-	using TR = BlendTraits<C>;
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	__shared__ __align__(16) float s_w[kWarpsPerCta][32];
-
-	const int tid = threadIdx.x, lwarp = tid >> 5, lane = tid & 31;
-	const int tile = blockIdx.x / kCtasPerTile;
-	const int warp = (blockIdx.x % kCtasPerTile) * kWarpsPerCta + lwarp;
-	const int tile_x0 = (tile % tiles_x) * GSR_BLOCK_X, tile_y0 = (tile / tiles_x) * GSR_BLOCK_Y;
-	int bx, by;
-	warp_block_origin(warp, bx, by);
-	const int px = tile_x0 + bx + (lane & 7), py = tile_y0 + by + (lane >> 3);
-	const bool inside = px < W && py < H;
-	const float pixf_x = (float)px, pixf_y = (float)py;
-	const size_t plane = (size_t)H * W;
-	const size_t pix_id = (size_t)W * py + px;
-
-	const uint2 range = ranges[tile];
-	const float T_final = inside ? final_Ts[pix_id] : 0.f;
-	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
-	int warp_last = last_contributor;
-#pragma unroll
-	for (int s = 16; s >= 1; s >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, s));
-	warp_last = min(warp_last, (int)(range.y - range.x));
-	if (warp_last == 0) return;
-
-	float g[C];
-	float gd = 0.f, gu = 0.f, bg_dot = 0.f;
-#pragma unroll
-	for (int ch = 0; ch < C; ch++) {
-		g[ch] = inside ? dL_dpixels[ch * plane + pix_id] : 0.f;
-		bg_dot += bg[ch] * g[ch];
-	}
-	if (inside) {
-		gd = dL_dpixel_depths[pix_id];
-		gu = dL_dpixel_uncs[pix_id];
-	}
-	float gcol[32];
-	{
-		const float *src = dL_dpixels + (size_t)lane * plane;
-		const int x0 = tile_x0 + bx, y0 = tile_y0 + by;
-		const bool vec_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0) && (x0 + 8 <= W);
-#pragma unroll
-		for (int rr = 0; rr < 4; rr++) {
-			const int y = y0 + rr;
-			if (vec_ok && y < H) {
-				const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)W * y + x0);
-				const float4 a4 = __ldg(p4), b4 = __ldg(p4 + 1);
-				gcol[rr * 8 + 0] = a4.x; gcol[rr * 8 + 1] = a4.y; gcol[rr * 8 + 2] = a4.z; gcol[rr * 8 + 3] = a4.w;
-				gcol[rr * 8 + 4] = b4.x; gcol[rr * 8 + 5] = b4.y; gcol[rr * 8 + 6] = b4.z; gcol[rr * 8 + 7] = b4.w;
-			} else {
-#pragma unroll
-				for (int cc = 0; cc < 8; cc++) {
-					const int x = x0 + cc;
-					gcol[rr * 8 + cc] = (x < W && y < H) ? __ldg(src + (size_t)W * y + x) : 0.f;
-				}
-			}
-		}
-	}
-
-	float T = T_final;
-	float X = 0.f, last_alpha = 0.f, last_dot = 0.f;
-	const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
-	const float neg_Tfinal_bg = -T_final * bg_dot;
-	// the previous contributing entry's 8 scalar terms, reduced one iteration late
-	float pv[8];
-#pragma unroll
-	for (int i = 0; i < 8; i++) pv[i] = 0.f;
-	uint32_t pid = 0;
-	bool have_prev = false;
-	const bool owner = vowner<8>(lane);
-	const int my_q = vidx<8>(lane);
-
-	using Feed = WarpFeed<C, true, false>;
-	Feed feed;
-	feed.init(smem_raw + (size_t)lwarp * TR::kWarpBytes, point_list + range.x, warp_last, rec, features, warp, lane, packed != 0);
-	feed.fill();
-	int m_cur = feed.issue(0);
-	int chunk = 0;
-	for (; m_cur > 0; chunk++) {
-		feed.fill();
-		const int m_next = feed.issue((chunk + 1) & 1);
-		feed.wait(chunk, m_cur);
-		__syncwarp();
-		const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
-		for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats) {
-			const uint32_t slot = (feed.done + e) & (kRing - 1);
-			const int pos = (int)feed.q_pos[slot];
-			const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
-			const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
-			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
-			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
-			const bool maybe = (pos < last_contributor) && !(power > 0.0f);
-			const float G = expf(power);
-			const float alpha = min(0.99f, __fmul_rn(r1.y, G));
-			const bool valid = maybe && !(alpha < kAlphaMin);
-			// flush the previous entry: its shuffle chain overlaps this entry's geometry above (same basic block: the RED is
-			// predicated, not branched around)
-			{
-				float t[8];
-#pragma unroll
-				for (int i = 0; i < 8; i++) t[i] = pv[i];
-				warp_transpose_reduce<8>(t, lane);
-				red_add_if(have_prev && owner, gacc + (size_t)pid * 8 + my_q, t[0]);
-				have_prev = false;
-			}
-			if (!__any_sync(0xffffffffu, valid)) continue;
-
-			float w = 0.f, rinv = 0.f;
-			if (valid) {
-				rinv = __frcp_rn(__fsub_rn(1.f, alpha)); // T <- T / (1 - alpha), CR/backward.cu:533
-				T = T * rinv;
-				w = alpha * T;
-			}
-			const uint32_t id = feed.q_id[slot];
-			// colour sums first (they need only w): lane = channel, weights through shared memory, one coalesced 128-B RED
-			s_w[lwarp][lane] = w;
-			__syncwarp();
-			{
-				float s0 = 0.f, s1 = 0.f;
-				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[lwarp]);
-#pragma unroll
-				for (int q = 0; q < 8; q++) {
-					const float4 ww = w4[q];
-					s0 += ww.x * gcol[4 * q + 0];
-					s1 += ww.y * gcol[4 * q + 1];
-					s0 += ww.z * gcol[4 * q + 2];
-					s1 += ww.w * gcol[4 * q + 3];
-				}
-				red_add(dL_dcolors + (size_t)id * C + lane, s0 + s1);
-			}
-			__syncwarp();
-#pragma unroll
-			for (int i = 0; i < 8; i++) pv[i] = 0.f;
-			if (valid) {
-				float d0 = r1.z * gd + r1.w * gu;
-				const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
-#pragma unroll
-				for (int q = 0; q < C / 4; q++) {
-					const float4 f = f4[q];
-					d0 += f.x * g[4 * q + 0];
-					d0 += f.y * g[4 * q + 1];
-					d0 += f.z * g[4 * q + 2];
-					d0 += f.w * g[4 * q + 3];
-				}
-				X = last_alpha * last_dot + (1.f - last_alpha) * X;
-				last_dot = d0;
-				float dL_dalpha = (d0 - X) * T;
-				last_alpha = alpha;
-				dL_dalpha += neg_Tfinal_bg * rinv;
-				const float dL_dG = r1.y * dL_dalpha;
-				const float gdx = G * d.x, gdy = G * d.y;
-				const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-				const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-				pv[0] = dL_dG * dG_ddelx * ddelx_dx;
-				pv[1] = dL_dG * dG_ddely * ddely_dy;
-				pv[2] = -0.5f * gdx * d.x * dL_dG;
-				pv[3] = -0.5f * gdx * d.y * dL_dG;
-				pv[4] = -0.5f * gdy * d.y * dL_dG;
-				pv[5] = G * dL_dalpha;
-				pv[6] = w * gd;
-				pv[7] = w * gu;
-			}
-			pid = id;
-			have_prev = true;
-		}
-		feed.done += m_cur;
-		__syncwarp();
-		m_cur = m_next;
-	}
-	feed.drain(chunk, 0);
-	if (have_prev) {
-		warp_transpose_reduce<8>(pv, lane);
-		if (owner) red_add(gacc + (size_t)pid * 8 + my_q, pv[0]);
-	}
-}
-#endif
 
 template <int C>
 static size_t bwd_smem_bytes()
@@ -733,22 +446,7 @@ cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *range
 #endif
 	switch (C) {
 	case 3: return launch_bwd<3>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
-#if GSR_BWD_DEFER
-	case 32: {
-		static bool configured = false;
-		if (!configured) {
-			cudaError_t e = cudaFuncSetAttribute(blend_backward_defer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes<32>());
-			if (e != cudaSuccess) return e;
-			configured = true;
-		}
-		blend_backward_defer_kernel<<<tiles * kCtasPerTile, 32 * kWarpsPerCta, bwd_smem_bytes<32>(), stream>>>(
-		    ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
-		count_launch();
-		return cudaGetLastError();
-	}
-#else
 	case 32: return launch_bwd<32>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
-#endif
 	default: return cudaErrorInvalidValue;
 	}
 }

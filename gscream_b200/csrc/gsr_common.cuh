@@ -152,10 +152,5 @@ __device__ __forceinline__ void red_add(float *addr, float a)
 {
 	asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
-// predicated form: no branch around the RED, so the surrounding code stays one basic block for the scheduler
-__device__ __forceinline__ void red_add_if(bool pred, float *addr, float a)
-{
-	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(a), "r"((unsigned)pred) : "memory");
-}
 
 } // namespace gsr
