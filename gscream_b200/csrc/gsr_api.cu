@@ -10,7 +10,6 @@
 #include "gsr_optim.cuh"
 #include <atomic>
 #include <cmath>
-#include <vector>
 
 namespace gsr {
 
@@ -502,28 +501,36 @@ int gsr_adam_step(int n_tensors, const gsr_adam_tensor *tensors_host, gsr_stream
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	if (n_tensors < 0 || (n_tensors > 0 && !tensors_host)) return GSR_E_BADARG;
-	std::vector<AdamTensor> tab;
-	tab.reserve((size_t)n_tensors);
+	// validate everything before the first launch: a bad descriptor must not leave the model half-updated
 	for (int k = 0; k < n_tensors; k++) {
 		const gsr_adam_tensor &a = tensors_host[k];
 		if (a.numel < 0 || a.step < 1) return GSR_E_BADARG;
-		if (a.numel == 0) continue;
-		if (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq) return GSR_E_BADARG;
-		AdamTensor t;
-		t.param = a.param; t.grad = a.grad; t.exp_avg = a.exp_avg; t.exp_avg_sq = a.exp_avg_sq; t.n = a.numel;
-		const double bc1 = 1.0 - std::pow(a.beta1, (double)a.step), bc2 = 1.0 - std::pow(a.beta2, (double)a.step);
-		t.one_minus_beta1 = (float)(1.0 - a.beta1);
-		t.beta2 = (float)a.beta2;
-		t.one_minus_beta2 = (float)(1.0 - a.beta2);
-		t.eps = (float)a.eps;
-		t.weight_decay = (float)a.weight_decay;
-		t.step_size = (float)(a.lr / bc1);
-		t.bias_correction2_sqrt = (float)std::sqrt(bc2);
-		t.pad = 0;
-		tab.push_back(t);
+		if (a.numel > 0 && (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq)) return GSR_E_BADARG;
+		if (!(a.beta1 >= 0.0 && a.beta1 < 1.0) || !(a.beta2 >= 0.0 && a.beta2 < 1.0)) return GSR_E_BADARG;
 	}
 	StageTimer timer(kOptim, stream);
-	GSR_CUDA(launch_adam_step((int)tab.size(), tab.data(), stream));
+	AdamTensor tab[kAdamMaxTensors];   // no heap: the C ABI never throws
+	int m = 0;
+	for (int k = 0; k < n_tensors; k++) {
+		const gsr_adam_tensor &a = tensors_host[k];
+		if (a.numel > 0) {
+			AdamTensor &t = tab[m++];
+			t.param = a.param; t.grad = a.grad; t.exp_avg = a.exp_avg; t.exp_avg_sq = a.exp_avg_sq; t.n = a.numel;
+			const double bc1 = 1.0 - std::pow(a.beta1, (double)a.step), bc2 = 1.0 - std::pow(a.beta2, (double)a.step);
+			t.one_minus_beta1 = (float)(1.0 - a.beta1);
+			t.beta2 = (float)a.beta2;
+			t.one_minus_beta2 = (float)(1.0 - a.beta2);
+			t.eps = (float)a.eps;
+			t.weight_decay = (float)a.weight_decay;
+			t.step_size = (float)(a.lr / bc1);
+			t.bias_correction2_sqrt = (float)std::sqrt(bc2);
+			t.pad = 0;
+		}
+		if (m == kAdamMaxTensors || (k == n_tensors - 1 && m > 0)) {
+			GSR_CUDA(launch_adam_step(m, tab, stream));
+			m = 0;
+		}
+	}
 	return 0;
 }
 
