@@ -19,6 +19,25 @@ def cpu_deep_copy_tuple(input_tuple):
     return tuple(copied_tensors)
 
 
+def _call_native(fn, args, debug, dump_name, message, **kwargs):
+    """Debug mode of the reference binding (diff_gaussian_rasterization/__init__.py:87-95, 150-158): CPU-clone the positional
+    arguments before the call can corrupt them, and on any exception save them as a snapshot, print the hint and re-raise."""
+    if not debug:
+        return fn(*args, **kwargs)
+    cpu_args = cpu_deep_copy_tuple(args)
+    try:
+        return fn(*args, **kwargs)
+    except Exception as ex:
+        torch.save(cpu_args, dump_name)
+        print(message)
+        raise ex
+
+
+def _or_empty(t):
+    """`None` inputs travel as empty CPU tensors -> null pointers in the native call (reference :230-240)."""
+    return torch.Tensor([]) if t is None else t
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, uncertainties, scales, rotations,
                         cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, uncertainties, scales,
@@ -36,16 +55,9 @@ class _RasterizeGaussians(torch.autograd.Function):
             raster_settings.tanfovx, raster_settings.tanfovy, raster_settings.image_height, raster_settings.image_width,
             sh, raster_settings.sh_degree, raster_settings.campos, raster_settings.prefiltered, raster_settings.debug,
         )
-        if raster_settings.debug:
-            cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
-            try:
-                num_rendered, color, depth, uncertainty, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
-            except Exception as ex:
-                torch.save(cpu_args, "snapshot_fw.dump")
-                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
-                raise ex
-        else:
-            num_rendered, color, depth, uncertainty, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+        num_rendered, color, depth, uncertainty, radii, geomBuffer, binningBuffer, imgBuffer = _call_native(
+            _C.rasterize_gaussians, args, raster_settings.debug, "snapshot_fw.dump",
+            "\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
 
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered
@@ -67,18 +79,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raster_settings.sh_degree, raster_settings.campos, geomBuffer, num_rendered, binningBuffer, imgBuffer,
                 raster_settings.debug)
         want_cov = cov3Ds_precomp.numel() != 0
-        if raster_settings.debug:
-            cpu_args = cpu_deep_copy_tuple(args)
-            try:
-                (grad_means2D, grad_colors_precomp, grad_opacities, grad_uncertainties, grad_means3D, grad_cov3Ds_precomp,
-                 grad_sh, grad_scales, grad_rotations) = _C.rasterize_gaussians_backward(*args, want_cov3D=want_cov)
-            except Exception as ex:
-                torch.save(cpu_args, "snapshot_bw.dump")
-                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
-                raise ex
-        else:
-            (grad_means2D, grad_colors_precomp, grad_opacities, grad_uncertainties, grad_means3D, grad_cov3Ds_precomp,
-             grad_sh, grad_scales, grad_rotations) = _C.rasterize_gaussians_backward(*args, want_cov3D=want_cov)
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_uncertainties, grad_means3D, grad_cov3Ds_precomp,
+         grad_sh, grad_scales, grad_rotations) = _call_native(
+            _C.rasterize_gaussians_backward, args, raster_settings.debug, "snapshot_bw.dump",
+            "\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n", want_cov3D=want_cov)
 
         # an input that was passed as an empty placeholder gets no gradient
         def _g(grad, inp):
@@ -137,46 +141,21 @@ class GaussianRasterizer(nn.Module):
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
 
-        if shs is None:
-            shs = torch.Tensor([])
-        if colors_precomp is None:
-            colors_precomp = torch.Tensor([])
-        if scales is None:
-            scales = torch.Tensor([])
-        if rotations is None:
-            rotations = torch.Tensor([])
-        if cov3D_precomp is None:
-            cov3D_precomp = torch.Tensor([])
-
-        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, uncertainties, scales, rotations,
-                                   cov3D_precomp, raster_settings)
+        return rasterize_gaussians(means3D, means2D, _or_empty(shs), _or_empty(colors_precomp), opacities, uncertainties,
+                                   _or_empty(scales), _or_empty(rotations), _or_empty(cov3D_precomp), raster_settings)
 
     def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
-        raster_settings = self.raster_settings
-        if scales is None:
-            scales = torch.Tensor([])
-        if rotations is None:
-            rotations = torch.Tensor([])
-        if cov3D_precomp is None:
-            cov3D_precomp = torch.Tensor([])
         with torch.no_grad():
-            radii = _C.rasterize_aussians_filter(
-                means3D, scales, rotations, raster_settings.scale_modifier, cov3D_precomp, raster_settings.viewmatrix,
-                raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy, raster_settings.image_height,
-                raster_settings.image_width, raster_settings.prefiltered, raster_settings.debug)
-        return radii
+            return _C.rasterize_aussians_filter(*self._filter_args(means3D, scales, rotations, cov3D_precomp))
 
     def position2D_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
-        raster_settings = self.raster_settings
-        if scales is None:
-            scales = torch.Tensor([])
-        if rotations is None:
-            rotations = torch.Tensor([])
-        if cov3D_precomp is None:
-            cov3D_precomp = torch.Tensor([])
         with torch.no_grad():
             radii, position2D_x, position2D_y = _C.rasterize_aussians_filter_position2D(
-                means3D, scales, rotations, raster_settings.scale_modifier, cov3D_precomp, raster_settings.viewmatrix,
-                raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy, raster_settings.image_height,
-                raster_settings.image_width, raster_settings.prefiltered, raster_settings.debug)
+                *self._filter_args(means3D, scales, rotations, cov3D_precomp))
         return radii, position2D_x, position2D_y
+
+    def _filter_args(self, means3D, scales, rotations, cov3D_precomp):
+        """The 13 positional arguments shared by the two anchor filters (rasterize_points.h:74-104)."""
+        rs = self.raster_settings
+        return (means3D, _or_empty(scales), _or_empty(rotations), rs.scale_modifier, _or_empty(cov3D_precomp), rs.viewmatrix,
+                rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, rs.prefiltered, rs.debug)
