@@ -141,3 +141,42 @@ def test_scene_generator_is_deterministic_and_matches_reference_camera_conventio
     assert P[3, 2] == 1.0 and torch.isclose(P[2, 2], torch.tensor((0.01 + 100.0) / (100.0 - 0.01)))  # graphics_utils.py:69-72
     yaw = scenes.make_camera(320, 180, yaw_deg=10.0)
     assert torch.allclose(yaw["viewmatrix"][:3, :3] @ yaw["viewmatrix"][:3, :3].t(), torch.eye(3), atol=1e-6)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """The drop-in boundary is a C ABI: include/gsr_b200.h must compile as C99 and as C++ with no CUDA or torch headers."""
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for compiler, std, suffix in (("gcc", "-std=c99", ".c"), ("g++", "-std=c++11", ".cpp")):
+        if shutil.which(compiler) is None:
+            pytest.fail("%s is part of the image" % compiler)
+        src = tmp_path / ("abi_probe" + suffix)
+        src.write_text('#include "gsr_b200.h"\nint probe(void) { gsr_adam_tensor t; t.numel = 0; return gsr_abi_version() + (int)sizeof(t); }\n')
+        r = subprocess.run([compiler, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_ctypes_prototypes_match_header_declarations():
+    """Every prototype of gscream_b200._lib.PROTOTYPES has the argument count and the argument classes (pointer / int / int64 /
+    size_t / float) of its declaration in include/gsr_b200.h."""
+    from gscream_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "gsr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decls = dict(re.findall(r"GSR_API\s+[\w\s\*]+?\b(gsr_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S))
+    assert set(decls) == set(_lib.PROTOTYPES), set(decls) ^ set(_lib.PROTOTYPES)
+    def ctype_of(param):
+        param = param.strip()
+        if "*" in param or param.startswith("gsr_stream_t"):
+            return ctypes.c_void_p
+        base = param.split()[:-1] if len(param.split()) > 1 else param.split()
+        base = " ".join(b for b in base if b != "const")
+        return {"int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t}[base]
+
+    for name, params in decls.items():
+        params = params.strip()
+        plist = [] if params in ("", "void") else [p for p in params.split(",") if p.strip()]
+        bound = _lib.PROTOTYPES[name][1]
+        assert len(plist) == len(bound), (name, len(plist), len(bound))
+        for i, (p, b) in enumerate(zip(plist, bound)):
+            assert ctype_of(p) is b, "%s argument %d (%s): header says %s, ctypes binds %s" % (name, i, p.strip(), ctype_of(p).__name__, b.__name__)
