@@ -243,3 +243,18 @@ def test_gpu_depth_losses_train_step_size_vs_fp64_closed_forms():
     err = np.abs(x.grad.double().cpu().numpy() - g64)
     scale = np.abs(g64).max()
     assert int((err > 2e-5 * scale).sum()) <= 32, int((err > 2e-5 * scale).sum())
+
+
+def test_depth_losses_validate_arguments_and_have_no_cpu_path():
+    from gscream_b200 import losses
+    d, y = torch.rand(1, 8, 9), torch.rand(1, 8, 9)
+    for fn in (lambda: losses.aligned_depth_losses(d, y), lambda: losses.multiscale_gradient_loss(d, y), lambda: losses.gradient_loss(d, y, torch.ones(1, 8, 9)),
+               lambda: losses.aligned_depth_l1(d, y)):
+        with pytest.raises(TypeError, match="no CPU loss path"):
+            fn()
+    with pytest.raises(NotImplementedError):
+        losses.aligned_depth_losses(d, y.requires_grad_(True))
+    # the reference signature: gradient_loss(prediction, target, mask[, reduction]) — train.py:232
+    import inspect
+    assert list(inspect.signature(losses.gradient_loss).parameters) == ["prediction", "target", "mask"]
+    assert list(inspect.signature(losses.aligned_depth_losses).parameters) == ["depth", "target", "fit_mask", "l1_mask", "grad_mask", "n_scales"]
