@@ -6,11 +6,23 @@ rasterize_points.cu:35-373 of W-Ted/GScream, but every byte of compute goes thro
 libgsr_b200.so (include/gsr_b200.h).  Torch is used only to own device memory and to name the
 current stream, which is what rasterize_points.cu does with libtorch.
 """
+import os
+
 import torch
 
 from . import _lib
 
 _PINNED = {}
+
+
+def _compiled():
+    """`GSR_GLUE=cpp`: route the five reference entry points through the compiled pybind11 glue (csrc/gsr_torch_glue.cpp, the
+    C++ counterpart of the reference's rasterize_points.cu above the same C ABI) instead of this module's ctypes marshalling.
+    Read at call time so that tests can compare the two glues in one process."""
+    if os.environ.get("GSR_GLUE", "ctypes") != "cpp":
+        return None
+    from . import _glue
+    return _glue.load()
 
 
 def _ptr(t):
@@ -52,6 +64,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, uncertaintys, scal
                         sh, degree, campos, prefiltered, debug):
     """RasterizeGaussiansCUDA, rasterize_points.cu:35-122.  Returns
     (num_rendered, color[C,H,W], depth[1,H,W], uncertainty[1,H,W], radii[P], geomBuffer, binningBuffer, imgBuffer)."""
+    native = _compiled()
+    if native is not None:
+        return native.rasterize_gaussians(background, means3D, colors, opacity, uncertaintys, scales, rotations, float(scale_modifier),
+                                          cov3D_precomp, viewmatrix, projmatrix, float(tan_fovx), float(tan_fovy), int(image_height),
+                                          int(image_width), sh, int(degree), campos, bool(prefiltered), bool(debug))
     lib = _lib.load()
     _check_means(means3D)
     if not means3D.is_cuda:
@@ -111,6 +128,12 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     gscream_b200.dist accumulate several views into one flat gradient bucket; `want_cov3D=False` skips
     writing dL_dcov3D when scales/rotations were given (the reference always materialises it even though
     nothing consumes it in that case) and returns None in its place."""
+    native = _compiled() if (out is None and not accumulate) else None
+    if native is not None:   # the reference's 23 positional arguments; dL_dcov3D is always materialised, like upstream
+        return native.rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, float(scale_modifier), cov3D_precomp,
+                                                   viewmatrix, projmatrix, float(tan_fovx), float(tan_fovy), dL_dout_color, dL_dout_depth,
+                                                   dL_dout_uncertainty, sh, int(degree), campos, geomBuffer, int(R), binningBuffer,
+                                                   imageBuffer, bool(debug))
     lib = _lib.load()
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
@@ -167,6 +190,10 @@ def _filter_common(means3D, scales, rotations, cov3D_precomp, viewmatrix, projma
 def rasterize_aussians_filter(means3D, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
                               tan_fovx, tan_fovy, image_height, image_width, prefiltered, debug):
     """RasterizeGaussiansfilterCUDA (sic), rasterize_points.cu:235-299 -> radii[P] int32."""
+    native = _compiled()
+    if native is not None:
+        return native.rasterize_aussians_filter(means3D, scales, rotations, float(scale_modifier), cov3D_precomp, viewmatrix, projmatrix,
+                                                float(tan_fovx), float(tan_fovy), int(image_height), int(image_width), bool(prefiltered), bool(debug))
     lib = _lib.load()
     _check_means(means3D)
     dev = means3D.device
@@ -188,6 +215,11 @@ def rasterize_aussians_filter(means3D, scales, rotations, scale_modifier, cov3D_
 def rasterize_aussians_filter_position2D(means3D, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
                                          tan_fovx, tan_fovy, image_height, image_width, prefiltered, debug):
     """RasterizeGaussiansfilterPositionCUDA, rasterize_points.cu:304-373 -> (radii, x, y)."""
+    native = _compiled()
+    if native is not None:
+        return native.rasterize_aussians_filter_position2D(means3D, scales, rotations, float(scale_modifier), cov3D_precomp, viewmatrix,
+                                                           projmatrix, float(tan_fovx), float(tan_fovy), int(image_height), int(image_width),
+                                                           bool(prefiltered), bool(debug))
     lib = _lib.load()
     _check_means(means3D)
     dev = means3D.device
@@ -210,6 +242,9 @@ def rasterize_aussians_filter_position2D(means3D, scales, rotations, scale_modif
 
 def mark_visible(means3D, viewmatrix, projmatrix):
     """markVisible, rasterize_points.cu:213-232 -> bool[P]."""
+    native = _compiled()
+    if native is not None:
+        return native.mark_visible(means3D, viewmatrix, projmatrix)
     lib = _lib.load()
     dev = means3D.device
     with torch.cuda.device(dev):
