@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libgsr_b200.so")
-SOURCES = ["gsr_api.cu", "gsr_preprocess.cu", "gsr_binning.cu", "gsr_sort.cu", "gsr_blend_fwd.cu", "gsr_blend_bwd.cu", "gsr_blend_bwd_mma.cu", "gsr_decode.cu", "gsr_loss.cu", "gsr_optim.cu"]
+SOURCES = ["gsr_api.cu", "gsr_preprocess.cu", "gsr_binning.cu", "gsr_sort.cu", "gsr_blend_fwd.cu", "gsr_blend_bwd.cu", "gsr_decode.cu", "gsr_loss.cu", "gsr_optim.cu"]
 HEADERS = ["gsr_common.cuh", "gsr_internal.cuh", "gsr_blend.cuh", "gsr_sort.cuh", "gsr_decode.cuh", "gsr_loss.cuh", "gsr_optim.cuh", os.path.join("..", "..", "include", "gsr_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

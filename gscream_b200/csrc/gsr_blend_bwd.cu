@@ -13,15 +13,23 @@
 //     is collapsed, by linearity in ch, into ONE scalar recurrence on X = sum_ch accum_rec[ch]*g[ch]:
 //         X <- last_alpha*last_dot + (1-last_alpha)*X,   dL_dalpha = (dot - X) * T,   dot = f_j . g_p
 //     so a pixel needs only its gradient row g_p (C+2 registers) and three scalars.
-//   * Per-Gaussian sums over the warp's 32 pixels are formed on chip before touching global memory:
-//     the 8 geometric/scalar terms by a transpose-reduce butterfly (9 shuffles instead of 40), and, for
-//     C = 32, the C colour terms by switching roles — lane l owns channel l and holds the gradient
-//     COLUMN of its warp's 32 pixels in registers, the per-pixel weights alpha*T go through 128 B of
-//     shared memory, and the warp issues a single coalesced 128-B red.global.add per Gaussian.
-//     That is one RED instruction per (warp, Gaussian) where the reference issues 32 x C scalar atomics.
-//   * Same warp-private feed as the forward kernel (gsr_blend.cuh: per-warp list scan by the instance masks, private
-//     double-buffered cp.async gather, no block barrier), run back to front and started at the warp's own deepest last
-//     contributor — nothing behind it can receive gradient.
+//   * Every term the reference adds atomically is linear in two per-(pixel, Gaussian) scalars,
+//         s = G * dL_dalpha      and      w = alpha * T,
+//     with coefficients that depend only on the Gaussian's record and the pixel's position / gradient row.  A warp
+//     therefore works on a landed chunk of its feed (gsr_blend.cuh) in two phases:
+//       phase 1 (lane = pixel, sequential in depth): the recurrence; leaves s and w of every (entry, pixel) of the chunk
+//                in 4 KB of shared memory.  Nothing in it waits for a reduction.
+//       phase 2 (entries independent): the per-Gaussian sums over the warp's 32 pixels.  The 8 geometric / scalar terms are
+//                rebuilt from s, w and the staged record and reduced by a transpose-reduce butterfly over TWO entries at a
+//                time (16 shuffles per pair, the first level free of selects because the upper half-warp loads the pair
+//                swapped); the C = 32 colour terms by switching roles — lane l owns channel l and holds the gradient COLUMN
+//                of the warp's 32 pixels in registers — ending in one coalesced 128-B red.global.add per (warp, Gaussian)
+//                where the reference issues 32 x C scalar atomics.
+//     Round 1 ran both per entry, the butterfly's 9 dependent shuffles and the colour sums' FMA chain on the recurrence's
+//     critical path: 63 % issue-slot utilisation at 16 warps per SM (profiles/r1_blend_v7_summary.md).  Separating the phases
+//     lets ptxas interleave independent entries' chains (profiles/r2_blend_bwd.md).
+//   * Same warp-private feed as the forward kernel (per-warp list scan by the instance masks, private double-buffered
+//     cp.async gather, no block barrier), run back to front and started at the warp's own deepest last contributor.
 //
 // Scalar terms are accumulated into gacc[P][8] = {dmean2D.x, dmean2D.y, dconic.x, dconic.y, dconic.w,
 // dopacity, ddepth, duncertainty}; colours into dL_dcolors[P][C].  Both must be zero (or hold the
@@ -29,42 +37,18 @@
 #include "gsr_blend.cuh"
 #include "gsr_internal.cuh"
 
-#ifndef GSR_BWD_RCP
-#define GSR_BWD_RCP 1
-#endif
-#ifndef GSR_BWD_ACC4
-#define GSR_BWD_ACC4 0
-#endif
-// C = 32: evaluate the two 32x32 products per (warp, chunk) on the tensor pipe (gsr_blend_bwd_mma.cu) instead of FFMA
-#ifndef GSR_BWD_MMA
-#define GSR_BWD_MMA 0
-#endif
-// C = 32: keep the lane = channel copy of the gradient block (the column each lane needs for the colour sums) in shared
-// memory instead of 32 registers per lane: ~96 registers -> 20 warps per SM instead of 16, for 8 more LDS.128 per pair
-#ifndef GSR_BWD_GCOL_SMEM
-#define GSR_BWD_GCOL_SMEM 0
-#endif
-// load the next entry's record (two LDS.128) one iteration ahead of its use: measured slower (2.32 vs 2.18 ms, 8 B of spill)
-#ifndef GSR_BWD_PREFETCH
-#define GSR_BWD_PREFETCH 0
-#endif
-// two partial sums in the lane = channel colour sums: -1 % (2.153 vs 2.178 ms); four (GSR_BWD_ACC4) are slower
-#ifndef GSR_BWD_PB2
-#define GSR_BWD_PB2 1
-#endif
-
-
 namespace gsr {
 
 constexpr int kWarpsPerCta = GSR_BWD_WARPS_PER_CTA;
 constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 
-// Transpose-reduce: every lane contributes N values; afterwards v[0] on lane l is the warp-wide total
-// of value index vidx<N>(l).  N/2 + N/4 + ... + 1 exchanges, then plain xor-adds for the remaining strides.
-template <int N>
+// Transpose-reduce over the lane-index bits S, S/2, ..: every lane contributes N values; afterwards v[0] on lane l is
+// the total (over the lanes that differ from l in those bits and all lower ones) of value index vidx<N, S>(l).
+// N/2 + N/4 + ... + 1 exchanges, then plain xor-adds for the remaining strides.
+template <int N, int S>
 __device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane)
 {
-	int s = 16;
+	int s = S;
 #pragma unroll
 	for (int n = N / 2; n >= 1; n >>= 1, s >>= 1) {
 		const bool upper = (lane & s) != 0;
@@ -78,42 +62,68 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane)
 #pragma unroll
 	for (; s >= 1; s >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], s);
 }
-template <int N>
+template <int N, int S>
 __device__ __forceinline__ int vidx(int lane)
 {
-	int idx = 0, s = 16;
+	int idx = 0, s = S;
 #pragma unroll
 	for (int n = N / 2; n >= 1; n >>= 1, s >>= 1)
 		if (lane & s) idx += n;
 	return idx;
 }
-template <int N>
-__device__ __forceinline__ bool vowner(int lane)
+
+// The eight geometric / scalar terms of one (pixel, Gaussian) pair (CR/backward.cu:557-601) from s = G dL_dalpha and
+// w = alpha T:  dL_dG G = opacity * s, so
+//   dmean2D.x = -(o s) (dx a + dy b) W/2, dmean2D.y = -(o s) (dy c + dx b) H/2, dconic = -1/2 (o s) {dx dx, dx dy, dy dy},
+//   dopacity = s, ddepth = w g_depth, duncertainty = w g_unc.
+__device__ __forceinline__ void pair_terms(const float *ent, float s, float w, float pixf_x, float pixf_y, float gd, float gu,
+                                           float half_w, float half_h, float *v)
 {
-	// the lowest lane among those holding the same total
-	int rest = 32 / N - 1; // mask of the low bits not consumed by the exchange steps
-	return (lane & rest) == 0;
+	const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
+	const float2 r1 = *reinterpret_cast<const float2 *>(ent + 4); // c o
+	const float dx = r0.x - pixf_x, dy = r0.y - pixf_y;
+	const float u = r1.y * s;
+	const float udx = u * dx, udy = u * dy;
+	v[0] = -(udx * r0.z + udy * r0.w) * half_w;
+	v[1] = -(udy * r1.x + udx * r0.w) * half_h;
+	v[2] = -0.5f * udx * dx;
+	v[3] = -0.5f * udx * dy;
+	v[4] = -0.5f * udy * dy;
+	v[5] = s;
+	v[6] = w * gd;
+	v[7] = w * gu;
 }
 
-// C = 32 keeps a 34-float gradient row and a 32-float gradient column per lane: 124 registers, 2 CTAs/SM (forcing 3
-// spills 108 B and is 18 % slower, profiles/r1_occupancy_ab.md).  Small C fits 3.
-// feature rows by per-entry TMA bulk copies instead of 16-B cp.async (C = 32): A/B in profiles/r1_feed_ab.md section 6
-#ifndef GSR_BWD_FEED_BULK
-#define GSR_BWD_FEED_BULK 0
-#endif
+// C = 32 keeps a 34-float gradient row and a 32-float gradient column per lane: 2 CTAs of 8 warps' worth of registers per
+// SM (16 warps); C <= 8 fits 3.
 #ifndef GSR_BWD_MINBLOCKS
 #define GSR_BWD_MINBLOCKS(C) ((C) <= 8 ? 3 : 2)
 #endif
-#if GSR_BWD_GCOL_SMEM
-#ifndef GSR_BWD_GCOL_WARPS
-#define GSR_BWD_GCOL_WARPS 20
-#endif
-#define GSR_BWD_MINCTAS(C) ((C) == 32 ? (GSR_BWD_GCOL_WARPS / kWarpsPerCta) : GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
-#elif defined(GSR_BWD_MINCTAS32)
-#define GSR_BWD_MINCTAS(C) ((C) == 32 ? GSR_BWD_MINCTAS32 : GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
-#else
 #define GSR_BWD_MINCTAS(C) (GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
+
+// entries of a chunk whose state-independent parts are computed side by side in phase 1
+#ifndef GSR_BWD_SUB
+#define GSR_BWD_SUB 2
 #endif
+constexpr int kSub = GSR_BWD_SUB;
+static_assert(kChunk % kSub == 0, "sub-batches tile the chunk");
+
+// 1 / d for d in [0.01, 1]: MUFU.RCP + one Newton step, no range check (__frcp_rn's slow path is a call behind a branch)
+__device__ __forceinline__ float rcp_1ulp(float d)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+	const float e = __fmaf_rn(-d, r, 1.f);
+	return __fmaf_rn(r, e, r);
+}
+
+template <int C>
+struct BwdSmem {
+	using TR = BlendTraits<C>;
+	static constexpr int kHandoffBytes = 2 * kChunk * 32 * 4; // s[kChunk][32], w[kChunk][32]
+	static constexpr int kWarpBytes = TR::kWarpBytes + kHandoffBytes;
+};
+
 template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_backward_kernel(
     const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
@@ -124,13 +134,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 {
 	using TR = BlendTraits<C>;
 	constexpr bool kLaneChannel = (C == 32); // colour sums by role switch; otherwise through the butterfly
-	constexpr bool kGcolSmem = kLaneChannel && (GSR_BWD_GCOL_SMEM != 0);
-	constexpr int kGcolStride = 36;
-	constexpr int NV = kLaneChannel ? 8 : 16;
 	static_assert(kLaneChannel || C <= 8, "butterfly path carries at most 8 colour channels");
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	__shared__ __align__(16) float s_w[kWarpsPerCta][32];
 
 	const int tid = threadIdx.x, lwarp = tid >> 5, lane = tid & 31;
 	const int tile = blockIdx.x / kCtasPerTile;
@@ -168,13 +174,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 		gu = dL_dpixel_uncs[pix_id];
 	}
 	// role switch (C == 32): lane l also holds channel l's gradient for the warp's 32 pixels
-	float gcol[(kLaneChannel && !kGcolSmem) ? 32 : 1];
-	float *s_gc = reinterpret_cast<float *>(smem_raw + (size_t)kWarpsPerCta * (TR::kWarpBytes + ((GSR_BWD_FEED_BULK != 0 && C > 3) ? 16 : 0))) + lwarp * 32 * kGcolStride; // [ch][36]
-	if (kGcolSmem) {
-#pragma unroll
-		for (int ch = 0; ch < C; ch++) s_gc[ch * kGcolStride + lane] = g[ch];
-		__syncwarp();
-	} else if (kLaneChannel) {
+	float gcol[kLaneChannel ? 32 : 1];
+	if (kLaneChannel) {
 		const float *src = dL_dpixels + (size_t)lane * plane;
 		const int x0 = tile_x0 + bx, y0 = tile_y0 + by;
 		const bool vec_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0) && (x0 + 8 <= W);
@@ -184,39 +185,33 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 			if (vec_ok && y < H) {
 				const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)W * y + x0);
 				const float4 a4 = __ldg(p4), b4 = __ldg(p4 + 1);
-				gcol[rr * 8 + 0] = a4.x; gcol[rr * 8 + 1] = a4.y; gcol[rr * 8 + 2] = a4.z; gcol[rr * 8 + 3] = a4.w;
-				gcol[rr * 8 + 4] = b4.x; gcol[rr * 8 + 5] = b4.y; gcol[rr * 8 + 6] = b4.z; gcol[rr * 8 + 7] = b4.w;
+				gcol[(rr * 8 + 0) % (kLaneChannel ? 32 : 1)] = a4.x; gcol[(rr * 8 + 1) % (kLaneChannel ? 32 : 1)] = a4.y;
+				gcol[(rr * 8 + 2) % (kLaneChannel ? 32 : 1)] = a4.z; gcol[(rr * 8 + 3) % (kLaneChannel ? 32 : 1)] = a4.w;
+				gcol[(rr * 8 + 4) % (kLaneChannel ? 32 : 1)] = b4.x; gcol[(rr * 8 + 5) % (kLaneChannel ? 32 : 1)] = b4.y;
+				gcol[(rr * 8 + 6) % (kLaneChannel ? 32 : 1)] = b4.z; gcol[(rr * 8 + 7) % (kLaneChannel ? 32 : 1)] = b4.w;
 			} else {
 #pragma unroll
 				for (int cc = 0; cc < 8; cc++) {
 					const int x = x0 + cc;
-					gcol[rr * 8 + cc] = (x < W && y < H) ? __ldg(src + (size_t)W * y + x) : 0.f;
+					gcol[(rr * 8 + cc) % (kLaneChannel ? 32 : 1)] = (x < W && y < H) ? __ldg(src + (size_t)W * y + x) : 0.f;
 				}
 			}
 		}
 	}
 
-	// packed copies (GSR_FFMA2, C == 32): the gradient row and column as register pairs for fma.rn.f32x2
-	constexpr bool kPacked = (GSR_FFMA2 != 0) && kLaneChannel && !kGcolSmem;
-	constexpr int kPairs = kPacked ? C / 2 : 1;
-	uint64_t g2[kPairs], gcol2[kPairs];
-	if (kPacked) {
-#pragma unroll
-		for (int i = 0; i < kPairs; i++) {
-			g2[i] = pack2(g[(2 * i) % C], g[(2 * i + 1) % C]);
-			gcol2[i] = pack2(gcol[(2 * i) % (kPacked ? 32 : 1)], gcol[(2 * i + 1) % (kPacked ? 32 : 1)]);
-		}
-	}
-
 	float T = T_final;
 	float X = 0.f, last_alpha = 0.f, last_dot = 0.f;
-	const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
+	const float half_w = 0.5 * W, half_h = 0.5 * H;
 	const float neg_Tfinal_bg = -T_final * bg_dot; // background term: (-T_final / (1 - alpha)) * sum_ch bg[ch] g[ch]
 
+	unsigned char *warp_smem = smem_raw + (size_t)lwarp * BwdSmem<C>::kWarpBytes;
+	float *s_s = reinterpret_cast<float *>(warp_smem + TR::kWarpBytes); // [kChunk][32]
+	float *s_w = s_s + kChunk * 32;                                     // [kChunk][32]
+
 	// back to front (CR/backward.cu:500): the feed scans list positions warp_last-1 .. 0
-	using Feed = WarpFeed<C, true, (GSR_BWD_FEED_BULK != 0) && (C > 3)>;
+	using Feed = WarpFeed<C, true>;
 	Feed feed;
-	feed.init(smem_raw + (size_t)lwarp * (TR::kWarpBytes + Feed::kExtraBytes), point_list + range.x, warp_last, rec, features, warp, lane, packed != 0);
+	feed.init(warp_smem, point_list + range.x, warp_last, rec, features, warp, lane, packed != 0);
 	feed.fill();
 	int m_cur = feed.issue(0);
 	int chunk = 0;
@@ -225,191 +220,140 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 		const int m_next = feed.issue((chunk + 1) & 1);
 		feed.wait(chunk, m_cur);
 		__syncwarp(); // every lane's copies of this chunk have landed
-		const float *ent = feed.stage + (chunk & 1) * TR::kStageFloats;
-#if GSR_BWD_PREFETCH
-		float4 r0n = *reinterpret_cast<const float4 *>(ent), r1n = *reinterpret_cast<const float4 *>(ent + 4);
-#endif
-		for (int e = 0; e < m_cur; e++, ent += TR::kEntryFloats) {
-			const uint32_t slot = (feed.done + e) & (kRing - 1);
-			const int pos = (int)feed.q_pos[slot]; // 0-based list position
-#if GSR_BWD_PREFETCH
-			const float4 r0 = r0n, r1 = r1n;     // this entry's record was loaded during the previous iteration
-			if (e + 1 < m_cur) {
-				r0n = *reinterpret_cast<const float4 *>(ent + TR::kEntryFloats);
-				r1n = *reinterpret_cast<const float4 *>(ent + TR::kEntryFloats + 4);
-			}
-#else
-			const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
-			const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
-#endif
-			const float2 d = {r0.x - pixf_x, r0.y - pixf_y};
-			const float power = gaussian_power(r0.z, r0.w, r1.x, d.x, d.y);
-			const bool maybe = (pos < last_contributor) && !(power > 0.0f);
-			const float G = expf(power);
-			const float alpha = min(0.99f, __fmul_rn(r1.y, G));
-			const bool valid = maybe && !(alpha < kAlphaMin);
-			if (!__any_sync(0xffffffffu, valid)) continue;
+		const float *ent0 = feed.stage + (chunk & 1) * TR::kStageFloats;
 
-			float v[NV];
+		// ---- phase 1: the per-pixel recurrence over the chunk's entries, in depth order ----
+		// kSub entries at a time: (a) everything that does not depend on the pixel's running state — alpha, 1 / (1 - alpha), G
+		// and the dot product, kSub independent chains for the scheduler to interleave — then (b) the short carried chain
+		// (T, X).  An entry that does not touch the pixel is encoded as alpha = 0, rinv = 1, G = 0: the recurrence below then
+		// leaves T unchanged, hands X on unchanged (0 * dot + 1 * X') and produces s = w = 0, without a branch.
+		uint32_t live = 0; // bit e: some pixel of the warp received gradient from entry e
+		for (int e0 = 0; e0 < m_cur; e0 += kSub) {
+			float al[kSub], ri[kSub], Gs[kSub], dt[kSub];
 #pragma unroll
-			for (int i = 0; i < NV; i++) v[i] = 0.f;
-			float w = 0.f;
-			if (valid) {
-				// T <- T / (1 - alpha) (CR/backward.cu:533), as T * rcp(1 - alpha); the reciprocal also serves the
-				// background term
-#if GSR_BWD_RCP
-				const float rinv = __frcp_rn(__fsub_rn(1.f, alpha));
-				T = T * rinv;
-#else
-				const float one_minus = __fsub_rn(1.f, alpha);
-				T = __fdiv_rn(T, one_minus);
-#endif
-				w = alpha * T;
+			for (int b = 0; b < kSub; b++) {
+				const int e = e0 + b;
+				const float *ent = ent0 + e * TR::kEntryFloats; // (rows past m_cur hold stale but readable shared memory)
+				const int pos = (int)feed.q_pos[(feed.done + e) & (kRing - 1)]; // 0-based list position
+				const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
+				const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
+				const float dx = r0.x - pixf_x, dy = r0.y - pixf_y;
+				const float power = gaussian_power(r0.z, r0.w, r1.x, dx, dy);
+				const float G = expf(power);
+				const float alpha = min(0.99f, __fmul_rn(r1.y, G));
+				const bool valid = (e < m_cur) && (pos < last_contributor) && !(power > 0.0f) && !(alpha < kAlphaMin);
 				// dot = f_j . g_p over colour channels, depth and uncertainty
-#if GSR_BWD_ACC4
-				float d0 = r1.z * gd, d1 = r1.w * gu, d2 = 0.f, d3 = 0.f;
-#else
 				float d0 = r1.z * gd + r1.w * gu;
-				float &d1 = d0, &d2 = d0, &d3 = d0;
-#endif
 				if (TR::kFeatInRec) {
 					const float4 r2 = *reinterpret_cast<const float4 *>(ent + 8);
 					const float cb = ent[12];
-					if (C > 0) d2 += r2.z * g[0];
-					if (C > 1) d3 += r2.w * g[1 % C];
+					if (C > 0) d0 += r2.z * g[0];
+					if (C > 1) d0 += r2.w * g[1 % C];
 					if (C > 2) d0 += cb * g[2 % C];
-				} else if (kPacked) {
-					// two chains of packed FMAs (even / odd 16-B parts), four partial sums folded at the end
-					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
-					uint64_t da = pack2(d0, 0.f), db = 0ull;
-#pragma unroll
-					for (int q = 0; q < C / 4; q++) {
-						const float4 f = f4[q];
-						da = fma2(pack2(f.x, f.y), g2[(2 * q) % kPairs], da);
-						db = fma2(pack2(f.z, f.w), g2[(2 * q + 1) % kPairs], db);
-					}
-					float lo, hi;
-					unpack2(add2(da, db), lo, hi);
-					d0 = lo + hi;
 				} else {
+					float d1 = 0.f, d2 = 0.f, d3 = 0.f;
 					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
 #pragma unroll
 					for (int q = 0; q < C / 4; q++) {
 						const float4 f = f4[q];
-						d0 += f.x * g[4 * q + 0];
-						d1 += f.y * g[4 * q + 1];
-						d2 += f.z * g[4 * q + 2];
-						d3 += f.w * g[4 * q + 3];
+						d0 += f.x * g[(4 * q + 0) % C];
+						d1 += f.y * g[(4 * q + 1) % C];
+						d2 += f.z * g[(4 * q + 2) % C];
+						d3 += f.w * g[(4 * q + 3) % C];
 					}
+					d0 = (d0 + d1) + (d2 + d3);
 				}
-#if GSR_BWD_ACC4
-				const float dot = (d0 + d1) + (d2 + d3);
-#else
-				const float dot = d0;
-#endif
-				X = last_alpha * last_dot + (1.f - last_alpha) * X;
-				last_dot = dot;
-				float dL_dalpha = (dot - X) * T;
-				last_alpha = alpha;
-#if GSR_BWD_RCP
-				dL_dalpha += neg_Tfinal_bg * rinv;
-#else
-				if (bg_dot != 0.f) dL_dalpha += (-T_final / one_minus) * bg_dot;
-#endif
-
-				const float dL_dG = r1.y * dL_dalpha;
-				const float gdx = G * d.x, gdy = G * d.y;
-				const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-				const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-				v[0] = dL_dG * dG_ddelx * ddelx_dx;
-				v[1] = dL_dG * dG_ddely * ddely_dy;
-				v[2] = -0.5f * gdx * d.x * dL_dG;
-				v[3] = -0.5f * gdx * d.y * dL_dG;
-				v[4] = -0.5f * gdy * d.y * dL_dG;
-				v[5] = G * dL_dalpha;
-				v[6] = w * gd;
-				v[7] = w * gu;
-				if (!kLaneChannel) {
-#pragma unroll
-					for (int ch = 0; ch < C; ch++) v[8 + ch] = w * g[ch];
-				}
+				al[b] = valid ? alpha : 0.f;
+				ri[b] = valid ? rcp_1ulp(__fsub_rn(1.f, alpha)) : 1.f; // T / (1 - alpha) (CR/backward.cu:533) as T * rcp; also serves the background term
+				Gs[b] = valid ? G : 0.f;
+				dt[b] = valid ? d0 : 0.f;
+				if (__any_sync(0xffffffffu, valid)) live |= 1u << e;
 			}
-			const uint32_t id = feed.q_id[slot];
-
-			// The butterfly's 9 dependent shuffles and the colour sums below are independent, but ptxas keeps them apart whatever the
-			// source order (weights stored first, hand-interleaved levels, butterfly deferred into the next entry's geometry block:
-			// measured 2.158 / 2.158 / 2.476 ms against 2.148 ms, profiles/r1_bwd_order_ab.md; code at commit 63eca77).
-			warp_transpose_reduce<NV>(v, lane);
-			if (vowner<NV>(lane)) {
-				const int q = vidx<NV>(lane);
-				if (q < 8) red_add(gacc + (size_t)id * 8 + q, v[0]);
-				else if (q < 8 + C) red_add(dL_dcolors + (size_t)id * C + (q - 8), v[0]);
-			}
-			if (kLaneChannel) {
-				s_w[lwarp][lane] = w;
-				__syncwarp();
-#if GSR_BWD_ACC4
-				float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#elif GSR_BWD_PB2
-				float s0 = 0.f, s1 = 0.f;
-				float &s2 = s0, &s3 = s1;
-#else
-				float s0 = 0.f;
-				float &s1 = s0, &s2 = s0, &s3 = s0;
-#endif
-				const float4 *w4 = reinterpret_cast<const float4 *>(s_w[lwarp]);
-				if (kPacked) {
-					uint64_t sa = 0ull, sb = 0ull;
 #pragma unroll
-					for (int q = 0; q < 8; q++) {
-						const float4 ww = w4[q];
-						sa = fma2(pack2(ww.x, ww.y), gcol2[(2 * q) % kPairs], sa);
-						sb = fma2(pack2(ww.z, ww.w), gcol2[(2 * q + 1) % kPairs], sb);
-					}
-					float lo, hi;
-					unpack2(add2(sa, sb), lo, hi);
-					red_add(dL_dcolors + (size_t)id * C + lane, lo + hi); // 32 lanes -> one coalesced 128-B RED
-					__syncwarp();
-					continue;
+			for (int b = 0; b < kSub; b++) {
+				T *= ri[b];
+				const float Xn = last_alpha * last_dot + (1.f - last_alpha) * X;
+				const float dL_dalpha = (dt[b] - Xn) * T + neg_Tfinal_bg * ri[b];
+				s_s[(e0 + b) * 32 + lane] = Gs[b] * dL_dalpha;
+				s_w[(e0 + b) * 32 + lane] = al[b] * T;
+				X = Xn;
+				last_alpha = al[b];
+				last_dot = dt[b];
+			}
+		}
+		__syncwarp(); // s and w of the chunk are visible to every lane
+
+		// ---- phase 2: per-Gaussian sums over the warp's 32 pixels; entries are independent of each other ----
+		if (kLaneChannel) {
+			const bool up = (lane & 16) != 0;
+			while (live) {
+				const int eA = __ffs(live) - 1;
+				live &= live - 1;
+				const int eB = live ? __ffs(live) - 1 : -1;
+				live &= live - 1; // no-op on 0
+				// the upper half-warp takes the pair swapped, so that the first exchange level needs no selects
+				const int e_mine = up ? eB : eA, e_other = up ? eA : eB;
+				float mine[8], other[8];
+				{
+					const int em = max(e_mine, 0), eo = max(e_other, 0);
+					const float sm = e_mine >= 0 ? s_s[em * 32 + lane] : 0.f, wm = e_mine >= 0 ? s_w[em * 32 + lane] : 0.f;
+					const float so = e_other >= 0 ? s_s[eo * 32 + lane] : 0.f, wo = e_other >= 0 ? s_w[eo * 32 + lane] : 0.f;
+					pair_terms(ent0 + em * TR::kEntryFloats, sm, wm, pixf_x, pixf_y, gd, gu, half_w, half_h, mine);
+					pair_terms(ent0 + eo * TR::kEntryFloats, so, wo, pixf_x, pixf_y, gd, gu, half_w, half_h, other);
 				}
-				const float4 *c4 = reinterpret_cast<const float4 *>(s_gc + lane * kGcolStride);
+#pragma unroll
+				for (int i = 0; i < 8; i++) mine[i] += __shfl_xor_sync(0xffffffffu, other[i], 16);
+				warp_transpose_reduce<8, 8>(mine, lane);
+				if ((lane & 1) == 0 && e_mine >= 0) {
+					const uint32_t id = feed.q_id[(feed.done + e_mine) & (kRing - 1)];
+					red_add(gacc + (size_t)id * 8 + vidx<8, 8>(lane), mine[0]);
+				}
+				// colour sums, lane = channel: sum_p w[p] g[p][lane] for both entries (independent chains)
+				const float4 *wA = reinterpret_cast<const float4 *>(s_w + eA * 32);
+				const float4 *wB = reinterpret_cast<const float4 *>(s_w + max(eB, 0) * 32);
+				float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
 				for (int q = 0; q < 8; q++) {
-					const float4 ww = w4[q];
-					if (kGcolSmem) {
-						const float4 gc = c4[q];
-						s0 += ww.x * gc.x;
-						s1 += ww.y * gc.y;
-						s2 += ww.z * gc.z;
-						s3 += ww.w * gc.w;
-					} else {
-						s0 += ww.x * gcol[(4 * q + 0) % (kGcolSmem ? 1 : 32)];
-						s1 += ww.y * gcol[(4 * q + 1) % (kGcolSmem ? 1 : 32)];
-						s2 += ww.z * gcol[(4 * q + 2) % (kGcolSmem ? 1 : 32)];
-						s3 += ww.w * gcol[(4 * q + 3) % (kGcolSmem ? 1 : 32)];
-					}
+					const float4 wa = wA[q], wb = wB[q];
+					a0 += wa.x * gcol[(4 * q + 0) % (kLaneChannel ? 32 : 1)];
+					a1 += wa.y * gcol[(4 * q + 1) % (kLaneChannel ? 32 : 1)];
+					a0 += wa.z * gcol[(4 * q + 2) % (kLaneChannel ? 32 : 1)];
+					a1 += wa.w * gcol[(4 * q + 3) % (kLaneChannel ? 32 : 1)];
+					b0 += wb.x * gcol[(4 * q + 0) % (kLaneChannel ? 32 : 1)];
+					b1 += wb.y * gcol[(4 * q + 1) % (kLaneChannel ? 32 : 1)];
+					b0 += wb.z * gcol[(4 * q + 2) % (kLaneChannel ? 32 : 1)];
+					b1 += wb.w * gcol[(4 * q + 3) % (kLaneChannel ? 32 : 1)];
 				}
-#if GSR_BWD_ACC4
-				red_add(dL_dcolors + (size_t)id * C + lane, (s0 + s1) + (s2 + s3)); // 32 lanes -> one coalesced 128-B RED
-#elif GSR_BWD_PB2
-				red_add(dL_dcolors + (size_t)id * C + lane, s0 + s1);
-#else
-				red_add(dL_dcolors + (size_t)id * C + lane, s0);
-#endif
-				__syncwarp();
+				const uint32_t idA = feed.q_id[(feed.done + eA) & (kRing - 1)];
+				red_add(dL_dcolors + (size_t)idA * C + lane, a0 + a1); // 32 lanes -> one coalesced 128-B RED
+				if (eB >= 0) {
+					const uint32_t idB = feed.q_id[(feed.done + eB) & (kRing - 1)];
+					red_add(dL_dcolors + (size_t)idB * C + lane, b0 + b1);
+				}
+			}
+		} else {
+			while (live) {
+				const int e = __ffs(live) - 1;
+				live &= live - 1;
+				float v[16];
+				const float w = s_w[e * 32 + lane];
+				pair_terms(ent0 + e * TR::kEntryFloats, s_s[e * 32 + lane], w, pixf_x, pixf_y, gd, gu, half_w, half_h, v);
+#pragma unroll
+				for (int ch = 0; ch < 8; ch++) v[8 + ch] = ch < C ? w * g[ch % C] : 0.f;
+				warp_transpose_reduce<16, 16>(v, lane);
+				if ((lane & 1) == 0) {
+					const uint32_t id = feed.q_id[(feed.done + e) & (kRing - 1)];
+					const int q = vidx<16, 16>(lane);
+					if (q < 8) red_add(gacc + (size_t)id * 8 + q, v[0]);
+					else if (q < 8 + C) red_add(dL_dcolors + (size_t)id * C + (q - 8), v[0]);
+				}
 			}
 		}
 		feed.done += m_cur;
-		__syncwarp(); // the stage buffer and the ring slots of this chunk may be reused
+		__syncwarp(); // the stage buffer, the ring slots and the s / w rows of this chunk may be reused
 		m_cur = m_next;
 	}
 	feed.drain(chunk, 0);
-}
-
-template <int C>
-static size_t bwd_smem_bytes()
-{
-	return (size_t)kWarpsPerCta * (BlendTraits<C>::kWarpBytes + ((GSR_BWD_FEED_BULK != 0 && C > 3) ? 16 : 0) + ((C == 32 && GSR_BWD_GCOL_SMEM) ? 32 * 36 * 4 : 0));
 }
 
 template <int C>
@@ -418,15 +362,12 @@ static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *po
                               const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                               float *dL_dcolors, cudaStream_t stream)
 {
-	using TR = BlendTraits<C>;
-	static bool configured = false;
-	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes<C>());
-		if (e != cudaSuccess) return e;
-		configured = true;
-	}
-	blend_backward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, bwd_smem_bytes<C>(), stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
-	                                                                dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
+	constexpr int smem = kWarpsPerCta * BwdSmem<C>::kWarpBytes;
+	// (the attribute is per device and idempotent: set it on every launch rather than cache a per-process flag)
+	cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess) return e;
+	blend_backward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
+	                                                                                 dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
 	count_launch();
 	return cudaGetLastError();
 }
@@ -440,10 +381,6 @@ cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *range
 	const int tiles = tiles_x * tiles_y;
 	if (tiles <= 0) return cudaSuccess;
 	const int packed = point_list_packed(P) ? 1 : 0;
-#if GSR_BWD_MMA
-	if (C == 32)
-		return launch_blend_backward_mma(P, W, H, ranges, point_list, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
-#endif
 	switch (C) {
 	case 3: return launch_bwd<3>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
 	case 32: return launch_bwd<32>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);

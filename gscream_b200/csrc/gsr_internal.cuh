@@ -54,9 +54,5 @@ cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *range
                                   const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                                   const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                                   float *dL_dcolors, cudaStream_t stream);
-cudaError_t launch_blend_backward_mma(int P, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
-                                      const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
-                                      const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
-                                      float *dL_dcolors, cudaStream_t stream);
 
 } // namespace gsr
