@@ -61,15 +61,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // One warp's feed over its tile's list.  kReverse: scan back to front starting at list position n-1 (backward pass).
-// kBulk (C > 3 only): the 128-B feature rows travel by one cp.async.bulk (TMA, SASS UBLKCP) per entry, issued by the lane that
-// owns the entry and completing on the stage's mbarrier; records stay on 16-B cp.async.  The async proxy keeps the feature
-// traffic off the LSU pipe at the price of one serialised issue round per entry (A/B: profiles/r1_feed_ab.md section 6).
+// (A per-entry cp.async.bulk variant of the feature gather was measured in round 1 and lost: profiles/r1_feed_ab.md section 6.)
 // All members are warp-uniform except `lane`-dependent temporaries.
-template <int C, bool kReverse, bool kBulk = false>
+template <int C, bool kReverse>
 struct WarpFeed {
 	using TR = BlendTraits<C>;
-	static constexpr int kExtraBytes = kBulk ? 16 : 0;   // two mbarriers behind the ring
-	uint64_t *bars;
 	const uint32_t *list;      // point_list + range.x
 	const float *rec, *feat;
 	float *stage;              // [2][kChunk][kEntryFloats]
@@ -90,16 +86,6 @@ struct WarpFeed {
 		stage = reinterpret_cast<float *>(warp_smem);
 		q_id = reinterpret_cast<uint32_t *>(warp_smem + 2 * TR::kStageFloats * 4);
 		q_pos = q_id + kRing;
-		if constexpr (kBulk) {
-			static_assert(!kBulk || !TR::kFeatInRec, "bulk feature rows need C > 3");
-			bars = reinterpret_cast<uint64_t *>(q_pos + kRing);
-			if (lane_ == 0) {
-				mbar_init(&bars[0], 1);
-				mbar_init(&bars[1], 1);
-				mbar_fence_init();
-			}
-			__syncwarp();
-		}
 		list = list_; n = n_; rec = rec_; feat = feat_; warp = warp_; lane = lane_; packed = packed_;
 		next_scan = 0;
 		tail = issued = done = 0;
@@ -154,12 +140,7 @@ struct WarpFeed {
 					cp_async16(dst + e * TR::kEntryFloats + part * 4, rec + (size_t)q_id[(issued + e) & (kRing - 1)] * GSR_REC_FLOATS + part * 4);
 			}
 		}
-		if constexpr (kBulk) {
-			if (m > 0) {
-				if (lane == 0) mbar_arrive_expect_tx(&bars[s], (uint32_t)m * C * 4);
-				if (lane < m) bulk_g2s(dst + lane * TR::kEntryFloats + TR::kRecParts * 4, feat + (size_t)q_id[(issued + lane) & (kRing - 1)] * C, C * 4, &bars[s]);
-			}
-		} else if constexpr (!TR::kFeatInRec) {
+		if constexpr (!TR::kFeatInRec) {
 			constexpr int kPer = 32 / TR::kFeatParts;
 			static_assert(32 % TR::kFeatParts == 0, "feature row must split into a power-of-two number of 16-B parts");
 			const int le = lane / TR::kFeatParts, part = lane % TR::kFeatParts;
@@ -174,49 +155,37 @@ struct WarpFeed {
 		issued += m;
 		return m;
 	}
-	// chunk number `chunk` (m entries, gathered into stage chunk & 1) has landed for this lane; one more chunk may be in flight
-	__device__ __forceinline__ void wait(int chunk, int m)
-	{
-		cp_async_wait_but_one();
-		if constexpr (kBulk)
-			if (m > 0) mbar_wait(&bars[chunk & 1], (uint32_t)((chunk >> 1) & 1));
-	}
-	// before the warp retires: nothing may still be in flight into its shared memory (`m_pending` entries of chunk `chunk`)
-	__device__ __forceinline__ void drain(int chunk, int m_pending)
-	{
-		cp_async_wait_all();
-		if constexpr (kBulk)
-			if (m_pending > 0) mbar_wait(&bars[chunk & 1], (uint32_t)((chunk >> 1) & 1));
-	}
+	// the older of the (at most two) chunks in flight has landed for this lane
+	__device__ __forceinline__ void wait() { cp_async_wait_but_one(); }
+	// before the warp retires: nothing may still be in flight into its shared memory
+	__device__ __forceinline__ void drain() { cp_async_wait_all(); }
 };
 
-// Packed FP32 (sm_100: fma.rn.f32x2, SASS FFMA2): one instruction performs two independent IEEE round-to-nearest FMAs on the
-// halves of 64-bit register pairs, so the per-channel accumulations of the blend kernels (the same FMAs, bit for bit) take half the
-// instructions (forward 34 -> 17, backward 64 -> 32 per contributing pair).  Measured on B200 (profiles/r1_ffma2_ab.md): parity-green
-// and SLOWER — forward 0.874 -> 0.889 ms at 72 registers (0.963 ms at 64 registers, where the pair alignment forces spills and
-// ~20 register moves per entry), backward 2.147 -> 2.247 ms with 13 % fewer instructions: an FFMA2 occupies the FMA pipe like the two
-// FFMAs it replaces and has the longer dependent-issue latency, which is what the backward is bound by.  Kept behind the switch.
-#ifndef GSR_FFMA2
-#define GSR_FFMA2 0
-#endif
-__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+// ---- 3xTF32 on the legacy tensor path (mma.sync m16n8k8, SASS HMMA.1688.F32.TF32) ----------------------------------------
+// The dense per-(pixel block, chunk) products of the C = 32 blend kernels run here: x = hi + lo with hi = the top 19 bits of x
+// (what the tensor core reads of a 32-bit operand), lo = x - hi exact; hi*hi + lo*hi + hi*lo leaves ~2^-21 relative error per
+// product, far inside the 1e-5 parity gate (tests/test_gpu_parity.py).  tcgen05 is no option for a single warp with private
+// operands: it needs a CTA-wide 64/128-row tile in shared memory issued by one thread.
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
 {
-	uint64_t r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-	return r;
+	// (volatile: splits of loop-invariant register operands must stay inside the chunk loop — hoisted, they would double the
+	// registers those operands take)
+	asm volatile("and.b32 %0, %1, 0xffffe000;" : "=r"(hi) : "r"(__float_as_uint(x)));
+	lo = __float_as_uint(x - __uint_as_float(hi));
 }
-__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+// D += A B, m16n8k8; with g = lane >> 2, t = lane & 3:  A row-major a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
+// B b0 (k = t, n = g) b1 (k = t+4, n = g);  C/D c0 c1 (g, 2t), (g, 2t+1), c2 c3 (g+8, 2t), (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
-	uint64_t d;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-	return d;
+	asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+__device__ __forceinline__ void mma3_tf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t b0h, uint32_t b1h, uint32_t b0l, uint32_t b1l)
 {
-	uint64_t d;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-	return d;
+	mma_tf32(c, al, b0h, b1h);
+	mma_tf32(c, ah, b0l, b1l);
+	mma_tf32(c, ah, b0h, b1h);
 }
 
 // power = -0.5 (a dx^2 + c dy^2) - b dx dy, CR/forward.cu:524 / CR/backward.cu:524, with the rounding

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 	for (; m_cur > 0; chunk++) {
 		feed.fill();
 		const int m_next = feed.issue((chunk + 1) & 1);
-		feed.wait(chunk, m_cur);
+		feed.wait();
 		__syncwarp(); // every lane's copies of this chunk have landed
 		const float *ent0 = feed.stage + (chunk & 1) * TR::kStageFloats;
 
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 		__syncwarp(); // the stage buffer, the ring slots and the s / w rows of this chunk may be reused
 		m_cur = m_next;
 	}
-	feed.drain(chunk, 0);
+	feed.drain();
 }
 
 // ---- C = 32 -----------------------------------------------------------------------------------------------------------------
@@ -299,27 +299,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 //     M = sum_p s[p] {1, cx, cy, cx^2, cx cy, cy^2}
 // — a [16 x 32] x [32 x 8] product whose B operand is the same for every chunk and exact in TF32 — and ddepth / duncertainty are
 // columns 32, 33 of the colour product.  |ax| exceeds |dx| by at most 3.5, which bounds the cancellation in the map.
-__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
-{
-	// (volatile: the splits of the loop-invariant gradient operands must stay inside the chunk loop — hoisted, they would
-	// double the 72 registers those operands already take)
-	asm volatile("and.b32 %0, %1, 0xffffe000;" : "=r"(hi) : "r"(__float_as_uint(x)));
-	lo = __float_as_uint(x - __uint_as_float(hi)); // exact; the tensor core reads its top 19 bits
-}
-// D += A B, m16n8k8; with g = lane >> 2, t = lane & 3:  A row-major a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
-// B b0 (k = t, n = g) b1 (k = t+4, n = g);  C/D c0 c1 (g, 2t), (g, 2t+1), c2 c3 (g+8, 2t), (g+8, 2t+1)
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
-{
-	asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void mma3_tf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t b0h, uint32_t b1h, uint32_t b0l, uint32_t b1l)
-{
-	mma_tf32(c, al, b0h, b1h);
-	mma_tf32(c, ah, b0l, b1l);
-	mma_tf32(c, ah, b0h, b1h);
-}
 // pixel (or channel) index of k-step ks, slot (t, half)
 __device__ __forceinline__ int kperm(int ks, int t, int half) { return 16 * (ks >> 1) + 4 * t + 2 * (ks & 1) + half; }
 
@@ -461,7 +440,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 	for (; m_cur > 0; chunk++) {
 		feed.fill();
 		const int m_next = feed.issue((chunk + 1) & 1);
-		feed.wait(chunk, m_cur);
+		feed.wait();
 		__syncwarp(); // every lane's copies of this chunk have landed
 		const float *ent0 = feed.stage + (chunk & 1) * TR::kStageFloats;
 
@@ -629,7 +608,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 		__syncwarp(); // the stage buffer, the ring slots and the s / w rows of this chunk may be reused
 		m_cur = m_next;
 	}
-	feed.drain(chunk, 0);
+	feed.drain();
 }
 
 static cudaError_t launch_bwd32(int tiles, const uint2 *ranges, const uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
