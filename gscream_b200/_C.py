@@ -6,13 +6,18 @@ rasterize_points.cu:35-373 of W-Ted/GScream, but every byte of compute goes thro
 libgsr_b200.so (include/gsr_b200.h).  Torch is used only to own device memory and to name the
 current stream, which is what rasterize_points.cu does with libtorch.
 """
+import itertools
 import os
+import threading
 
 import torch
 
 from . import _lib
 
 _PINNED = {}
+_PINNED_LOCK = threading.Lock()
+_PINNED_SLOTS = 64
+_R_HINT = {}
 
 
 def _compiled():
@@ -48,10 +53,26 @@ def _stream():
 
 
 def _pinned_i64(device):
+    """A pinned int64 for one call's num_rendered.  Slots rotate through a small per-device ring, so that concurrent calls
+    (threads, streams) on one device never share a counter: a call waits for its own value before it returns, which frees
+    its slot long before the ring wraps."""
     key = (device.index if device.index is not None else torch.cuda.current_device())
-    if key not in _PINNED:
-        _PINNED[key] = torch.zeros(1, dtype=torch.int64).pin_memory()
-    return _PINNED[key]
+    with _PINNED_LOCK:
+        if key not in _PINNED:
+            _PINNED[key] = (torch.zeros(_PINNED_SLOTS, dtype=torch.int64).pin_memory(), itertools.count())
+        ring, counter = _PINNED[key]
+        return ring[next(counter) % _PINNED_SLOTS:][:1]
+
+
+def _capacity_guess(key):
+    """Instance capacity to size the binning buffer with BEFORE this call's num_rendered has reached the host: 25 % above the
+    (slowly decaying) running maximum of what this problem shape produced so far.  None: no history, take the exact path."""
+    hint = _R_HINT.get(key)
+    return None if hint is None else int(hint * 1.25) + 65536
+
+
+def _capacity_update(key, R):
+    _R_HINT[key] = max(float(R), 0.98 * _R_HINT.get(key, 0.0))
 
 
 def _check_means(means3D):
@@ -88,14 +109,17 @@ def rasterize_gaussians(background, means3D, colors, opacity, uncertaintys, scal
             raise RuntimeError("For non-RGB, provide precomputed Gaussian colors!")
 
         f32 = dict(dtype=torch.float32, device=dev)
-        out_color = torch.zeros((C, H, W), **f32)
-        out_depth = torch.zeros((1, H, W), **f32)
-        out_unc = torch.zeros((1, H, W), **f32)
-        radii = torch.zeros((P,), dtype=torch.int32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
-        if P == 0:  # rasterize_points.cu:85
+        if P == 0:  # rasterize_points.cu:85: nothing is launched, the images are the reference's torch::full(0)
             empty = torch.empty((0,), **u8)
-            return 0, out_color, out_depth, out_unc, radii, empty, empty.clone(), empty.clone()
+            return (0, torch.zeros((C, H, W), **f32), torch.zeros((1, H, W), **f32), torch.zeros((1, H, W), **f32),
+                    torch.zeros((0,), dtype=torch.int32, device=dev), empty, empty.clone(), empty.clone())
+        # every element of the four outputs is written by the kernels (the reference fills them with zeros first,
+        # rasterize_points.cu:69-72)
+        out_color = torch.empty((C, H, W), **f32)
+        out_depth = torch.empty((1, H, W), **f32)
+        out_unc = torch.empty((1, H, W), **f32)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
 
         geom = torch.empty((lib.gsr_geom_bytes(P),), **u8)
         img = torch.empty((lib.gsr_image_bytes(W, H),), **u8)
@@ -106,13 +130,28 @@ def rasterize_gaussians(background, means3D, colors, opacity, uncertaintys, scal
             _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix),
             _ptr(campos), W, H, float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), radii.data_ptr(),
             geom.data_ptr(), geom.numel(), pinned.data_ptr(), stream))
-        # the one host sync the reference API imposes: num_rendered is returned as a Python int
-        torch.cuda.current_stream().synchronize()
+        # The reference API returns num_rendered as a Python int and sizes the binning buffer from it: one blocking copy in the
+        # middle of the forward (CR/rasterizer_impl.cu:287) that drains the GPU's queue.  Here the second half is launched right
+        # behind the first with a buffer sized from an estimate (its kernels read num_rendered from device memory), and the host
+        # then waits for stage 1's counter only — the GPU keeps running.  A wrong estimate costs one repeat of the second half.
+        counted = torch.cuda.Event()
+        counted.record()
+
+        def second_half(num_rendered, capacity):
+            buf = torch.empty((lib.gsr_binning_bytes(P, capacity, W, H),), **u8)
+            _lib.check(lib.gsr_forward_stage2(
+                P, C, num_rendered, _ptr(colors), _ptr(background), W, H, geom.data_ptr(), geom.numel(), buf.data_ptr(), buf.numel(),
+                img.data_ptr(), img.numel(), out_color.data_ptr(), out_depth.data_ptr(), out_unc.data_ptr(), stream))
+            return buf
+
+        key = (dev.index, P, W, H)
+        guess = None if os.environ.get("GSR_EXACT_BINNING") else _capacity_guess(key)
+        binning = second_half(-1, guess) if guess is not None else None
+        counted.synchronize()
         R = int(pinned.item())
-        binning = torch.empty((lib.gsr_binning_bytes(P, R, W, H),), **u8)
-        _lib.check(lib.gsr_forward_stage2(
-            P, C, R, _ptr(colors), _ptr(background), W, H, geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(),
-            img.data_ptr(), img.numel(), out_color.data_ptr(), out_depth.data_ptr(), out_unc.data_ptr(), stream))
+        if binning is None or R > lib.gsr_binning_capacity(P, W, H, binning.numel()):
+            binning = second_half(R, R)
+        _capacity_update(key, R)
         if debug:  # CHECK_CUDA(debug), auxiliary.h:166-173
             torch.cuda.synchronize(dev)
     return R, out_color, out_depth, out_unc, radii, geom, binning, img
@@ -271,7 +310,7 @@ def debug_export(P, R, W, H, geomBuffer, binningBuffer, imageBuffer):
             final_T=torch.zeros((H * W,), dtype=torch.float32, device=dev),
             n_contrib=torch.zeros((H * W,), dtype=torch.int32, device=dev))
         _lib.check(lib.gsr_debug_export(
-            P, R, W, H, geomBuffer.data_ptr(), binningBuffer.data_ptr(), imageBuffer.data_ptr(), o["xy"].data_ptr(),
+            P, R, W, H, geomBuffer.data_ptr(), binningBuffer.data_ptr(), binningBuffer.numel(), imageBuffer.data_ptr(), o["xy"].data_ptr(),
             o["depths"].data_ptr(), o["conic_opacity"].data_ptr(), o["tiles_touched"].data_ptr(), o["point_list"].data_ptr(),
             o["ranges"].data_ptr(), o["final_T"].data_ptr(), o["n_contrib"].data_ptr(), _stream()))
         o["point_list"] = o["point_list"][:R]

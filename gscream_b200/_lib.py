@@ -19,6 +19,7 @@ PROTOTYPES = {
     "gsr_geom_bytes": (_sz, [_i]),
     "gsr_image_bytes": (_sz, [_i, _i]),
     "gsr_binning_bytes": (_sz, [_i, _i64, _i, _i]),
+    "gsr_binning_capacity": (_i64, [_i, _i, _i, _sz]),
     "gsr_forward_stage1": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
                                 _i, _i, _f, _f, _i, _vp, _vp, _sz, _vp, _vp]),
     "gsr_forward_stage2": (_i, [_i, _i, _i64, _vp, _vp, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
@@ -27,7 +28,7 @@ PROTOTYPES = {
     "gsr_visible_filter": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp]),
     "gsr_position2d_filter": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "gsr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
-    "gsr_debug_export": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsr_debug_export": (_i, [_i, _i64, _i, _i, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_decode_supported": (_i, [_i, _i]),
     "gsr_decode_scratch_bytes": (_sz, [_i]),
     "gsr_decode_stage1": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
@@ -80,7 +81,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.gsr_abi_version() != 1:
+    if lib.gsr_abi_version() != 2:
         raise GsrError("libgsr_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -56,9 +56,10 @@ __global__ void export_records_kernel(int P, const float *__restrict__ rec, floa
 
 // point_list entries carry the per-warp overlap mask in their top byte (gsr_common.cuh: point_list_packed); the export
 // returns plain Gaussian ids like the reference's point_list (CR/rasterizer_impl.h:55-62)
-__global__ void export_point_list_kernel(int64_t R, const uint32_t *__restrict__ src, uint32_t mask, uint32_t *__restrict__ dst)
+__global__ void export_point_list_kernel(int64_t R, const uint32_t *__restrict__ src, const uint32_t *__restrict__ header, uint32_t *__restrict__ dst)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t mask = header[kHdrPacked] ? 0x00FFFFFFu : 0xFFFFFFFFu;
 	if (i < R) dst[i] = src[i] & mask;
 }
 
@@ -95,6 +96,7 @@ const char *gsr_error_string(int code)
 size_t gsr_geom_bytes(int P) { return geom_layout(P).total; }
 size_t gsr_image_bytes(int width, int height) { return image_layout(width, height).total; }
 size_t gsr_binning_bytes(int P, int64_t num_rendered, int width, int height) { return binning_layout(P, num_rendered, width, height).total; }
+int64_t gsr_binning_capacity(int P, int width, int height, size_t binning_bytes) { return binning_capacity(P, width, height, binning_bytes); }
 
 int64_t gsr_launch_count(int reset)
 {
@@ -154,22 +156,26 @@ int gsr_forward_stage2(int P, int C, int64_t num_rendered, const float *colors_p
                        size_t image_bytes, float *out_color, float *out_depth, float *out_uncertainty, gsr_stream_t stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
-	if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return GSR_E_BADARG;
+	if (P < 0 || width <= 0 || height <= 0 || num_rendered < -1) return GSR_E_BADARG;
 	if (P == 0) return 0;
 	if (!channels_ok(C)) return GSR_E_CHANNELS;
 	if (!background || !geom_buffer || !binning_buffer || !image_buffer || !out_color || !out_depth || !out_uncertainty) return GSR_E_BADARG;
 	if (C > 3 && (!colors_precomp || !aligned16(colors_precomp))) return GSR_E_BADARG;
 	const GeomLayout GL = geom_layout(P);
 	const ImageLayout IL = image_layout(width, height);
-	const BinningLayout BL = binning_layout(P, num_rendered, width, height);
-	if (geom_bytes < GL.total || image_bytes < IL.total || binning_bytes < BL.total) return GSR_E_WORKSPACE;
+	// the binning buffer's layout follows from its size; num_rendered itself is read by the kernels from device memory
+	const int64_t capacity = binning_capacity(P, width, height, binning_bytes);
+	if (capacity < 1 || num_rendered > capacity) return GSR_E_WORKSPACE;
+	const BinningLayout BL = binning_layout(P, capacity, width, height);
+	if (geom_bytes < GL.total || image_bytes < IL.total) return GSR_E_WORKSPACE;
 	if (!aligned16(geom_buffer) || !aligned16(binning_buffer) || !aligned16(image_buffer)) return GSR_E_WORKSPACE;
 	char *geom = (char *)geom_buffer, *binning = (char *)binning_buffer, *image = (char *)image_buffer;
 
-	{ StageTimer t(kBin, stream); GSR_CUDA(bin_instances(P, num_rendered, width, height, geom, GL, binning, BL, image, IL, stream)); }
+	{ StageTimer t(kBin, stream); GSR_CUDA(bin_instances(P, capacity, width, height, geom, GL, binning, BL, image, IL, stream)); }
 	{
 		StageTimer t(kBlendFwd, stream);
-		GSR_CUDA(launch_blend_forward(C, P, width, height, (const uint2 *)(image + IL.ranges), (uint32_t *)(binning + BL.val[point_list_index(width, height)]),
+		GSR_CUDA(launch_blend_forward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.header),
+		                              (uint32_t *)(binning + BL.val[point_list_index(width, height)]),
 		                              (const float *)(geom + GL.rec), colors_precomp, background, (float *)(image + IL.final_T),
 		                              (uint32_t *)(image + IL.n_contrib), out_color, out_depth, out_uncertainty, stream));
 	}
@@ -198,8 +204,10 @@ int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const
 	if (shs && (!campos || !dL_dsh)) return GSR_E_BADARG;
 	const GeomLayout GL = geom_layout(P);
 	const ImageLayout IL = image_layout(width, height);
-	const BinningLayout BL = binning_layout(P, num_rendered, width, height);
-	if (geom_bytes < GL.total || image_bytes < IL.total || binning_bytes < BL.total) return GSR_E_WORKSPACE;
+	const int64_t capacity = binning_capacity(P, width, height, binning_bytes); // the layout the forward used for this buffer
+	if (capacity < 1 || num_rendered > capacity) return GSR_E_WORKSPACE;
+	const BinningLayout BL = binning_layout(P, capacity, width, height);
+	if (geom_bytes < GL.total || image_bytes < IL.total) return GSR_E_WORKSPACE;
 	char *geom = (char *)geom_buffer, *binning = (char *)binning_buffer, *image = (char *)image_buffer;
 
 	float *gacc = (float *)(geom + GL.gacc);
@@ -210,7 +218,8 @@ int gsr_backward(int P, int C, int sh_degree, int M, int64_t num_rendered, const
 	count_launch(2);
 	if (num_rendered > 0) {
 		StageTimer t(kBlendBwd, stream);
-		GSR_CUDA(launch_blend_backward(C, P, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
+		GSR_CUDA(launch_blend_backward(C, width, height, (const uint2 *)(image + IL.ranges), (const uint32_t *)(binning + BL.header),
+		                               (const uint32_t *)(binning + BL.val[point_list_index(width, height)]),
 		                               (const float *)(geom + GL.rec), colors_precomp, background, (const float *)(image + IL.final_T),
 		                               (const uint32_t *)(image + IL.n_contrib), dL_dout_color, dL_dout_depth, dL_dout_uncertainty, gacc,
 		                               dL_dcolors, stream));
@@ -535,14 +544,16 @@ int gsr_adam_step(int n_tensors, const gsr_adam_tensor *tensors_host, gsr_stream
 }
 
 int gsr_debug_export(int P, int64_t num_rendered, int width, int height, const void *geom_buffer, const void *binning_buffer,
-                     const void *image_buffer, float *xy, float *depths, float *conic_opacity, uint32_t *tiles_touched,
+                     size_t binning_bytes, const void *image_buffer, float *xy, float *depths, float *conic_opacity, uint32_t *tiles_touched,
                      uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib, gsr_stream_t stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	if (P <= 0 || width <= 0 || height <= 0) return GSR_E_BADARG;
 	const GeomLayout GL = geom_layout(P);
 	const ImageLayout IL = image_layout(width, height);
-	const BinningLayout BL = binning_layout(P, num_rendered, width, height);
+	const int64_t capacity = binning_buffer ? binning_capacity(P, width, height, binning_bytes) : 1;
+	if (capacity < 1 || num_rendered > capacity) return GSR_E_WORKSPACE;
+	const BinningLayout BL = binning_layout(P, capacity, width, height);
 	const char *geom = (const char *)geom_buffer, *binning = (const char *)binning_buffer, *image = (const char *)image_buffer;
 	const size_t N = (size_t)width * height;
 	const size_t tiles = (size_t)((width + GSR_BLOCK_X - 1) / GSR_BLOCK_X) * ((height + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y);
@@ -553,7 +564,7 @@ int gsr_debug_export(int P, int64_t num_rendered, int width, int height, const v
 	if (geom && tiles_touched) GSR_CUDA(cudaMemcpyAsync(tiles_touched, geom + GL.tiles_touched, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream));
 	if (binning && point_list && num_rendered > 0) {
 		export_point_list_kernel<<<(unsigned)((num_rendered + 255) / 256), 256, 0, stream>>>(
-		    num_rendered, (const uint32_t *)(binning + BL.val[point_list_index(width, height)]), point_list_packed(P) ? 0x00FFFFFFu : 0xFFFFFFFFu, point_list);
+		    num_rendered, (const uint32_t *)(binning + BL.val[point_list_index(width, height)]), (const uint32_t *)(binning + BL.header), point_list);
 		GSR_CUDA(cudaGetLastError());
 	}
 	if (image && ranges) GSR_CUDA(cudaMemcpyAsync(ranges, image + IL.ranges, tiles * 8, cudaMemcpyDeviceToDevice, stream));

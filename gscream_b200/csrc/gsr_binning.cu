@@ -18,17 +18,11 @@
 // Gaussian index) as well.  Depth keys are positive floats (z > 0.2), so their bit patterns order like
 // the values (CR/rasterizer_impl.cu:102-106).
 //
-// The stable radix sort and the prefix sum are hand-written (gsr_sort.cu).  Building with -DGSR_USE_CUB=1 swaps
-// in cub::DeviceRadixSort / cub::DeviceScan for A/B timing (profiles/r1_sort_ab.md); results are identical.
+// The stable radix sort and the prefix sum are hand-written (gsr_sort.cu; A/B against cub::DeviceRadixSort / DeviceScan in
+// round 1: profiles/r1_sort_ab.md, within +-8 %, identical results).
 #include "gsr_internal.cuh"
 #include "gsr_sort.cuh"
 #include <algorithm>
-#ifndef GSR_USE_CUB
-#define GSR_USE_CUB 0
-#endif
-#if GSR_USE_CUB
-#include <cub/cub.cuh>
-#endif
 
 namespace gsr {
 
@@ -40,54 +34,16 @@ static int tile_bits(int W, int H)
 	while ((1 << bits) < tiles) bits++;
 	return bits;
 }
-#if GSR_USE_CUB
-static size_t sort_temp_bytes(int64_t n)
-{
-	// Out-of-place radix sort: CUB needs an alternate key and value array plus histograms / look-back
-	// state.  The query needs a CUDA device; the closed-form bound keeps the layout well defined (and
-	// identical) where there is none, and CUB re-checks the size it is given at sort time.
-	const size_t nn = (size_t)std::max<int64_t>(n, 1);
-	size_t bytes = 0;
-	cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-	                                                (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)nn);
-	if (e != cudaSuccess) { bytes = 0; (void)cudaGetLastError(); }
-	return std::max(bytes, 8 * nn + (size_t(1) << 22));
-}
-struct GatherTiles { // tiles_touched gathered through the depth order, fed to the scan as an input iterator
-	const uint32_t *tiles_touched;
-	const uint32_t *order;
-	__device__ __forceinline__ uint32_t operator()(int i) const { return tiles_touched[order[i]]; }
-};
-using GatherIter = cub::TransformInputIterator<uint32_t, GatherTiles, cub::CountingInputIterator<int>>;
-static size_t scan_temp_bytes(int n)
-{
-	size_t bytes = 0;
-	GatherIter in(cub::CountingInputIterator<int>(0), GatherTiles{nullptr, nullptr});
-	cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, bytes, in, (uint32_t *)nullptr, std::max(n, 1));
-	if (e != cudaSuccess) { bytes = 0; (void)cudaGetLastError(); }
-	return std::max(bytes, (size_t(1) << 20));
-}
-
-#endif
 
 // Where the sorted arrays end up ([0] or [1] of the ping-pong pairs): a pure function of the problem shape, so
 // forward, backward and the debug export agree without any state.
 int depth_order_index()
 {
-#if GSR_USE_CUB
-	return 1;
-#else
 	return radix_plan(1, 32).passes & 1; // 4 passes -> back in [0]
-#endif
 }
 int point_list_index(int W, int H)
 {
-#if GSR_USE_CUB
-	(void)W; (void)H;
-	return 1;
-#else
 	return radix_plan(1, tile_bits(W, H)).passes & 1;
-#endif
 }
 
 GeomLayout geom_layout(int P)
@@ -106,11 +62,7 @@ GeomLayout geom_layout(int P)
 	L.gacc = take(p * 32);
 	L.clamped = take(p * 3);
 	L.rgb = take(p * 12);
-#if GSR_USE_CUB
-	L.temp_bytes = std::max(sort_temp_bytes(P), scan_temp_bytes(P));
-#else
 	L.temp_bytes = radix_plan(P, 32).bytes + scan_scratch_bytes(P);
-#endif
 	L.temp = take(L.temp_bytes);
 	L.total = off;
 	return L;
@@ -137,16 +89,12 @@ BinningLayout binning_layout(int P, int64_t R, int W, int H)
 	size_t off = 0;
 	const size_t r = (size_t)std::max<int64_t>(R, 1);
 	auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+	L.header = take(256);
 	L.key[0] = take(r * 4);
 	L.key[1] = take(r * 4);
 	L.val[0] = take(r * 4);
 	L.val[1] = take(r * 4);
-#if GSR_USE_CUB
-	(void)W; (void)H;
-	L.temp_bytes = sort_temp_bytes(R);
-#else
 	L.temp_bytes = radix_plan(R, tile_bits(W, H)).bytes;
-#endif
 	L.temp = take(L.temp_bytes);
 	L.total = off;
 	return L;
@@ -166,11 +114,18 @@ BinningLayout binning_layout(int P, int64_t R, int W, int H)
 // alpha >= 1/255 bounding box touches (gsr_blend.cuh).
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t *__restrict__ order,
                                                              const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ tiles_touched,
-                                                             const float *__restrict__ rec, int gx, int gy, bool packed,
-                                                             uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+                                                             const float *__restrict__ rec, int gx, int gy, bool packed, int64_t capacity,
+                                                             uint32_t *__restrict__ header, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
 	const int lane = threadIdx.x & 31;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t R = __ldg(offsets + (P - 1)); // num_rendered: known on the device only (the host has not waited for it)
+	if (i == 0) { // the buffer describes itself: the backward pass and the debug export read the format from here
+		header[kHdrPacked] = packed ? 1u : 0u;
+		header[kHdrCount] = R;
+		header[kHdrOverflow] = (int64_t)R > capacity ? 1u : 0u;
+	}
+	if ((int64_t)R > capacity) return; // the caller sized the buffer from a guess that was too small: it re-runs this stage
 	uint32_t g = 0, tt = 0, incl = 0;
 	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
 	float2 xy = {0.f, 0.f}, ext = {-1.f, -1.f};
@@ -220,8 +175,11 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 }
 
 // identifyTileRanges, CR/rasterizer_impl.cu:116-138, on 32-bit tile ids; 8 sorted keys per thread (two 16-B loads).
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint32_t *__restrict__ keys, uint2 *__restrict__ ranges)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t capacity, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys,
+                                                          uint2 *__restrict__ ranges)
 {
+	if ((int64_t)__ldg(n_dev) > capacity) return; // overflow: every range stays (0, 0)
+	const int64_t L = (int64_t)__ldg(n_dev);
 	const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
 	if (base >= L) return;
 	uint32_t k[8];
@@ -256,32 +214,18 @@ cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStr
 {
 	if (P <= 0) return cudaSuccess;
 	cudaError_t e;
-#if GSR_USE_CUB
-	size_t temp = L.temp_bytes;
-	e = cub::DeviceRadixSort::SortPairs(geom + L.temp, temp, (const uint32_t *)(geom + L.depth_key[0]), (uint32_t *)(geom + L.depth_key[1]),
-	                                    (const uint32_t *)(geom + L.depth_val[0]), (uint32_t *)(geom + L.depth_val[1]), P, 0, 32, stream);
-	if (e != cudaSuccess) return e;
-	count_launch(5);
-	const uint32_t *order = (const uint32_t *)(geom + L.depth_val[1]);
-	GatherTiles op{(const uint32_t *)(geom + L.tiles_touched), order};
-	GatherIter in(cub::CountingInputIterator<int>(0), op);
-	temp = L.temp_bytes;
-	e = cub::DeviceScan::InclusiveSum(geom + L.temp, temp, in, (uint32_t *)(geom + L.offsets), P, stream);
-	if (e != cudaSuccess) return e;
-	count_launch(2);
-	return cudaGetLastError();
-#else
 	const int which = radix_sort_pairs((uint32_t *)(geom + L.depth_key[0]), (uint32_t *)(geom + L.depth_val[0]), (uint32_t *)(geom + L.depth_key[1]),
-	                                   (uint32_t *)(geom + L.depth_val[1]), P, 32, geom + L.temp, stream, &e);
+	                                   (uint32_t *)(geom + L.depth_val[1]), P, nullptr, 32, geom + L.temp, stream, &e);
 	if (e != cudaSuccess) return e;
 	const uint32_t *order = (const uint32_t *)(geom + L.depth_val[which]);
 	return inclusive_sum_gather((const uint32_t *)(geom + L.tiles_touched), order, (uint32_t *)(geom + L.offsets), P,
 	                            geom + L.temp + radix_plan(P, 32).bytes, stream);
-#endif
 }
 
-// Stage-2 head: emission, stable bucketing by tile id, ranges.
-cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const GeomLayout &GL,
+// Stage-2 head: emission, stable bucketing by tile id, ranges.  `capacity` is what the binning buffer was sized for; the
+// number of instances itself (num_rendered = offsets[P-1]) is read by the kernels from device memory, so nothing here waits
+// for the host to learn it.  If it exceeds the capacity the stage leaves every range empty and flags the buffer's header.
+cudaError_t bin_instances(int P, int64_t capacity, int W, int H, char *geom, const GeomLayout &GL,
                           char *binning, const BinningLayout &BL, char *image, const ImageLayout &IL, cudaStream_t stream)
 {
 	const int gx = (W + GSR_BLOCK_X - 1) / GSR_BLOCK_X, gy = (H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
@@ -289,32 +233,38 @@ cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const Geom
 	cudaError_t e = cudaMemsetAsync(image + IL.ranges, 0, (size_t)tiles * sizeof(uint2), stream); // CR/rasterizer_impl.cu:316
 	if (e != cudaSuccess) return e;
 	count_launch();
-	if (P <= 0 || R <= 0) return cudaSuccess;
+	if (P <= 0 || capacity <= 0) return cudaSuccess;
 
 	const uint32_t *order = (const uint32_t *)(geom + GL.depth_val[depth_order_index()]);
+	const uint32_t *n_dev = (const uint32_t *)(geom + GL.offsets) + (P - 1);
 	emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order, (const uint32_t *)(geom + GL.offsets),
 	                                                         (const uint32_t *)(geom + GL.tiles_touched), (const float *)(geom + GL.rec),
-	                                                         gx, gy, point_list_packed(P), (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
+	                                                         gx, gy, point_list_packed(P), capacity, (uint32_t *)(binning + BL.header),
+	                                                         (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
 	count_launch();
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
 
 	const int bits = tile_bits(W, H);
-#if GSR_USE_CUB
-	size_t temp = BL.temp_bytes;
-	e = cub::DeviceRadixSort::SortPairs(binning + BL.temp, temp, (const uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.key[1]),
-	                                    (const uint32_t *)(binning + BL.val[0]), (uint32_t *)(binning + BL.val[1]), (int)R, 0, bits, stream);
-	if (e != cudaSuccess) return e;
-	count_launch(1 + (bits + 7) / 8);
-	const int which = 1;
-#else
 	const int which = radix_sort_pairs((uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]), (uint32_t *)(binning + BL.key[1]),
-	                                   (uint32_t *)(binning + BL.val[1]), R, bits, binning + BL.temp, stream, &e);
+	                                   (uint32_t *)(binning + BL.val[1]), capacity, n_dev, bits, binning + BL.temp, stream, &e);
 	if (e != cudaSuccess) return e;
-#endif
-	tile_ranges_kernel<<<(unsigned)((R + 2047) / 2048), 256, 0, stream>>>(R, (const uint32_t *)(binning + BL.key[which]), (uint2 *)(image + IL.ranges));
+	tile_ranges_kernel<<<(unsigned)((capacity + 2047) / 2048), 256, 0, stream>>>(capacity, n_dev, (const uint32_t *)(binning + BL.key[which]), (uint2 *)(image + IL.ranges));
 	count_launch();
 	return cudaGetLastError();
+}
+
+// Largest instance count whose layout fits `bytes`: forward, backward and the debug export all derive the buffer's layout
+// from its size, so no capacity has to travel beside it.
+int64_t binning_capacity(int P, int W, int H, size_t bytes)
+{
+	if (binning_layout(P, 1, W, H).total > bytes) return 0;
+	int64_t lo = 1, hi = (int64_t)(bytes / 16) + 1; // layout(lo) fits, layout(hi) does not (16 B per instance alone exceed it)
+	while (hi - lo > 1) {
+		const int64_t mid = lo + (hi - lo) / 2;
+		if (binning_layout(P, mid, W, H).total <= bytes) lo = mid; else hi = mid;
+	}
+	return lo;
 }
 
 } // namespace gsr

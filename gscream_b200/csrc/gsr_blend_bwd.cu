@@ -126,7 +126,7 @@ struct BwdSmem {
 
 template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_backward_kernel(
-    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
+    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dpixel_uncs,
@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_b
 	const size_t pix_id = (size_t)W * py + px;
 
 	const uint2 range = ranges[tile];
+	const int packed = (int)__ldg(header + kHdrPacked); // format of the list entries, recorded by the instance emission
 	const float T_final = inside ? final_Ts[pix_id] : 0.f;
 	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
 
@@ -314,7 +315,7 @@ struct Bwd32Smem {
 #endif
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_backward_c32_kernel(
-    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, int packed, int W, int H, int tiles_x,
+    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dpixel_uncs,
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 	const size_t pix_id = (size_t)W * py + px;
 
 	const uint2 range = ranges[tile];
+	const int packed = (int)__ldg(header + kHdrPacked); // format of the list entries, recorded by the instance emission
 	const float T_final = inside ? final_Ts[pix_id] : 0.f;
 	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
 
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 	feed.drain();
 }
 
-static cudaError_t launch_bwd32(int tiles, const uint2 *ranges, const uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
+static cudaError_t launch_bwd32(int tiles, const uint2 *ranges, const uint32_t *point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x, const float *rec,
                                 const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                                 const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                                 float *dL_dcolors, cudaStream_t stream)
@@ -619,14 +621,14 @@ static cudaError_t launch_bwd32(int tiles, const uint2 *ranges, const uint32_t *
 	constexpr int smem = kWarpsPerCta * Bwd32Smem::kWarpBytes;
 	cudaError_t e = cudaFuncSetAttribute(blend_backward_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return e;
-	blend_backward_c32_kernel<<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
+	blend_backward_c32_kernel<<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
 	                                                                                  dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
 	count_launch();
 	return cudaGetLastError();
 }
 
 template <int C>
-static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, int packed, int W, int H, int tiles_x, const float *rec,
+static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x, const float *rec,
                               const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                               const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                               float *dL_dcolors, cudaStream_t stream)
@@ -635,13 +637,13 @@ static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *po
 	// (the attribute is per device and idempotent: set it on every launch rather than cache a per-process flag)
 	cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return e;
-	blend_backward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
+	blend_backward_kernel<C><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
 	                                                                                 dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
 	count_launch();
 	return cudaGetLastError();
 }
 
-cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, const uint32_t *header, const uint32_t *point_list, const float *rec,
                                   const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                                   const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                                   float *dL_dcolors, cudaStream_t stream)
@@ -649,10 +651,9 @@ cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *range
 	const int tiles_x = (W + GSR_BLOCK_X - 1) / GSR_BLOCK_X, tiles_y = (H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
 	const int tiles = tiles_x * tiles_y;
 	if (tiles <= 0) return cudaSuccess;
-	const int packed = point_list_packed(P) ? 1 : 0;
 	switch (C) {
-	case 3: return launch_bwd<3>(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
-	case 32: return launch_bwd32(tiles, ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+	case 3: return launch_bwd<3>(tiles, ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+	case 32: return launch_bwd32(tiles, ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
 	default: return cudaErrorInvalidValue;
 	}
 }

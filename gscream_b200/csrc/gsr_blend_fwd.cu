@@ -50,7 +50,7 @@ __device__ __forceinline__ void clear_unblended(const Feed &feed, uint32_t *list
 #endif
 template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINCTAS) blend_forward_kernel(
-    const uint2 *__restrict__ ranges, uint32_t *point_list, int packed, int W, int H, int tiles_x,
+    const uint2 *__restrict__ ranges, uint32_t *point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ bg,
     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
     float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_unc)
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD_MINCTAS) blend_forw
 	const float pixf_x = (float)px, pixf_y = (float)py;
 
 	const uint2 range = ranges[tile];
+	const int packed = (int)__ldg(header + kHdrPacked); // format of the list entries, recorded by the instance emission
 	float T = 1.0f;
 	uint32_t last_contributor = 0; // 1-based list position of the last blended Gaussian
 	uint32_t last_ring = 0;       // ... as 1 + ring index while its chunk is being blended
@@ -155,7 +156,7 @@ struct Fwd32Smem {
 #endif
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD32_MINCTAS) blend_forward_c32_kernel(
-    const uint2 *__restrict__ ranges, uint32_t *point_list, int packed, int W, int H, int tiles_x,
+    const uint2 *__restrict__ ranges, uint32_t *point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
     float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_unc)
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD32_MINCTAS) blend_fo
 	const float pixf_x = (float)px, pixf_y = (float)py;
 
 	const uint2 range = ranges[tile];
+	const int packed = (int)__ldg(header + kHdrPacked); // format of the list entries, recorded by the instance emission
 	float T = 1.0f;
 	uint32_t last_contributor = 0; // 1-based list position of the last blended Gaussian
 	uint32_t last_ring = 0;       // ... as 1 + ring index while its chunk is being blended
@@ -300,28 +302,27 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_FWD32_MINCTAS) blend_fo
 		}
 }
 
-cudaError_t launch_blend_forward(int C, int P, int W, int H, const uint2 *ranges, uint32_t *point_list, const float *rec,
+cudaError_t launch_blend_forward(int C, int W, int H, const uint2 *ranges, const uint32_t *header, uint32_t *point_list, const float *rec,
                                  const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
                                  float *out_depth, float *out_unc, cudaStream_t stream)
 {
 	const int tiles_x = (W + GSR_BLOCK_X - 1) / GSR_BLOCK_X, tiles_y = (H + GSR_BLOCK_Y - 1) / GSR_BLOCK_Y;
 	const int tiles = tiles_x * tiles_y;
 	if (tiles <= 0) return cudaSuccess;
-	const int packed = point_list_packed(P) ? 1 : 0;
 	cudaError_t e;
 	switch (C) {
 	case 3: {
 		constexpr int smem = kWarpsPerCta * BlendTraits<3>::kWarpBytes;
 		// (the attribute is per device and idempotent: set on every launch rather than cached in a per-process flag)
 		if ((e = cudaFuncSetAttribute(blend_forward_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-		blend_forward_kernel<3><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, bg, final_T, n_contrib,
+		blend_forward_kernel<3><<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, header, W, H, tiles_x, rec, bg, final_T, n_contrib,
 		                                                                                out_color, out_depth, out_unc);
 		break;
 	}
 	case 32: {
 		constexpr int smem = kWarpsPerCta * Fwd32Smem::kWarpBytes;
 		if ((e = cudaFuncSetAttribute(blend_forward_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-		blend_forward_c32_kernel<<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, packed, W, H, tiles_x, rec, features, bg, final_T,
+		blend_forward_c32_kernel<<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_T,
 		                                                                                 n_contrib, out_color, out_depth, out_unc);
 		break;
 	}

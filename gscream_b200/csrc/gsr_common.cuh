@@ -46,7 +46,8 @@ struct ImageLayout {    // "imgBuffer"
 	size_t ranges;       // uint2[tiles]
 	size_t total;
 };
-struct BinningLayout {  // "binningBuffer"
+struct BinningLayout {  // "binningBuffer"; R below is the CAPACITY the buffer was sized for (>= num_rendered)
+	size_t header;       // u32[64]: the buffer describes itself (kHdr*), written by the instance emission
 	size_t key[2];       // u32[R] x2 tile ids: [0] emitted, [1] sorted
 	size_t val[2];       // u32[R] x2 Gaussian ids: [0] emitted, [1] sorted = point_list
 	size_t temp;
@@ -54,9 +55,15 @@ struct BinningLayout {  // "binningBuffer"
 	size_t total;
 };
 
+// header words of the binning buffer
+constexpr int kHdrPacked = 0;    // 1: point_list entries carry the per-warp overlap mask above a 24-bit id, 0: plain ids
+constexpr int kHdrCount = 1;     // num_rendered as the device computed it
+constexpr int kHdrOverflow = 2;  // 1: num_rendered exceeded the buffer's capacity, the lists are empty
+
 GeomLayout geom_layout(int P);
 ImageLayout image_layout(int W, int H);
 BinningLayout binning_layout(int P, int64_t R, int W, int H);
+int64_t binning_capacity(int P, int W, int H, size_t bytes); // largest R whose layout fits `bytes`
 
 // ---- launch accounting ------------------------------------------------------------------
 void count_launch(int n = 1);

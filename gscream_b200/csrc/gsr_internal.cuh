@@ -43,14 +43,15 @@ cudaError_t launch_preprocess(int mode, const PreArgs &a, cudaStream_t stream);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t stream);
 cudaError_t launch_preprocess_backward(const PreBwdArgs &a, cudaStream_t stream);
 cudaError_t depth_order_and_scan(int P, char *geom, const GeomLayout &L, cudaStream_t stream);
-cudaError_t bin_instances(int P, int64_t R, int W, int H, char *geom, const GeomLayout &GL, char *binning, const BinningLayout &BL,
+cudaError_t bin_instances(int P, int64_t capacity, int W, int H, char *geom, const GeomLayout &GL, char *binning, const BinningLayout &BL,
                           char *image, const ImageLayout &IL, cudaStream_t stream);
 int depth_order_index();
 int point_list_index(int W, int H);
-cudaError_t launch_blend_forward(int C, int P, int W, int H, const uint2 *ranges, uint32_t *point_list, const float *rec,
+// (`header`: the binning buffer's self-description — the blend kernels read the point_list format from it)
+cudaError_t launch_blend_forward(int C, int W, int H, const uint2 *ranges, const uint32_t *header, uint32_t *point_list, const float *rec,
                                  const float *features, const float *bg, float *final_T, uint32_t *n_contrib, float *out_color,
                                  float *out_depth, float *out_unc, cudaStream_t stream);
-cudaError_t launch_blend_backward(int C, int P, int W, int H, const uint2 *ranges, const uint32_t *point_list, const float *rec,
+cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, const uint32_t *header, const uint32_t *point_list, const float *rec,
                                   const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                                   const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                                   float *dL_dcolors, cudaStream_t stream);

@@ -33,9 +33,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 // ------------------------------------------------------------------------------------------------
 // per-tile digit histogram of one pass (tiles are those of the CURRENT element order, so this runs per pass)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRsThreads) rs_histogram_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t mask, int tiles,
+__global__ void __launch_bounds__(kRsThreads) rs_histogram_kernel(const uint32_t *__restrict__ keys, int64_t n_cap, const uint32_t *__restrict__ n_dev, int shift, uint32_t mask, int tiles,
                                                                   uint32_t *__restrict__ counts, uint32_t *__restrict__ totals)
 {
+	const int64_t n = device_count(n_cap, n_dev);
 	__shared__ uint32_t s_hist[256];
 	const int t = threadIdx.x;
 	s_hist[t] = 0;
@@ -78,9 +79,12 @@ __global__ void __launch_bounds__(kRsThreads) rs_offsets_kernel(uint32_t *__rest
 
 // stable scatter of one digit pass
 __global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                                                                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
-                                                                int shift, int width, const uint32_t *__restrict__ offsets, int tiles)
+                                                                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_cap,
+                                                                const uint32_t *__restrict__ n_dev, int shift, int width,
+                                                                const uint32_t *__restrict__ offsets, int tiles)
 {
+	const int64_t n = device_count(n_cap, n_dev);
+	if ((int64_t)blockIdx.x * kRsTile >= n) return; // (uniform per block) nothing of this tile exists
 	const uint32_t mask = (1u << width) - 1u;
 	__shared__ uint32_t s_hist[8][256]; // per-warp digit counts, then per-warp base inside the tile
 	__shared__ uint32_t s_tile_start[256];
@@ -187,8 +191,8 @@ RadixPlan radix_plan(int64_t n, int bits)
 	return pl;
 }
 
-int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int bits, void *scratch,
-                     cudaStream_t stream, cudaError_t *err)
+int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, const uint32_t *n_dev, int bits,
+                     void *scratch, cudaStream_t stream, cudaError_t *err)
 {
 	*err = cudaSuccess;
 	if (n <= 0) return 0;
@@ -202,9 +206,9 @@ int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint3
 	for (int p = 0; p < pl.passes; p++) {
 		const int width = std::min(8, bits - 8 * p);
 		const uint32_t mask = (1u << width) - 1u;
-		rs_histogram_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, n, 8 * p, mask, pl.tiles, counts, totals + p * 256);
+		rs_histogram_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, n, n_dev, 8 * p, mask, pl.tiles, counts, totals + p * 256);
 		rs_offsets_kernel<<<256, kRsThreads, 0, stream>>>(counts, totals + p * 256, pl.tiles);
-		rs_scatter_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n, 8 * p, width, counts, pl.tiles);
+		rs_scatter_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n, n_dev, 8 * p, width, counts, pl.tiles);
 		count_launch(3);
 		std::swap(kin, kout);
 		std::swap(vin, vout);

@@ -37,8 +37,17 @@ RadixPlan radix_plan(int64_t n, int bits);
 // Sorts n pairs by the low `bits` bits of the key (stable).  keys_a/vals_a hold the input; the result lands in
 // (keys_a, vals_a) when the pass count is even and in (keys_b, vals_b) when it is odd — the return value tells
 // which (0 = a, 1 = b).  `scratch` must hold radix_plan(n, bits).bytes.  Launches on `stream`, never syncs.
-int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int bits, void *scratch,
-                     cudaStream_t stream, cudaError_t *err);
+// n_dev != nullptr: the element count is only known on the device (*n_dev, e.g. num_rendered); `n` is then the capacity the
+// arrays and the grids are sized for, and min(*n_dev, n) elements are sorted — no host round trip between the kernel that
+// produces the count and the sort.
+int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, const uint32_t *n_dev, int bits,
+                     void *scratch, cudaStream_t stream, cudaError_t *err);
+__device__ __forceinline__ int64_t device_count(int64_t cap, const uint32_t *n_dev)
+{
+	if (!n_dev) return cap;
+	const int64_t n = (int64_t)__ldg(n_dev);
+	return n < cap ? n : cap;
+}
 
 // Inclusive prefix sum of in[order[i]] (order may be null: in[i]) into out[0..n).  scratch: scan_scratch_bytes(n).
 size_t scan_scratch_bytes(int64_t n);

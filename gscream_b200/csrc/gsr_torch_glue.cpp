@@ -19,6 +19,7 @@
 #include <c10/cuda/CUDAGuard.h>
 
 #include <map>
+#include <ATen/cuda/CUDAEvent.h>
 #include <mutex>
 #include <tuple>
 
@@ -55,16 +56,35 @@ struct F32 {
 
 gsr_stream_t current_stream() { return (gsr_stream_t)at::cuda::getCurrentCUDAStream().stream(); }
 
-// one pinned int64 per device for num_rendered
+// a pinned int64 for one call's num_rendered: slots rotate through a small per-device ring, so that concurrent calls on one
+// device never share a counter (a call waits for its own value before it returns, long before the ring wraps)
+constexpr int kPinnedSlots = 64;
 int64_t *pinned_counter(int device)
 {
 	static std::mutex mu;
-	static std::map<int, Tensor> slots;
+	static std::map<int, std::pair<Tensor, int64_t>> rings;
 	std::lock_guard<std::mutex> lock(mu);
-	auto it = slots.find(device);
-	if (it == slots.end())
-		it = slots.emplace(device, torch::zeros({1}, torch::dtype(torch::kInt64).pinned_memory(true))).first;
-	return it->second.data_ptr<int64_t>();
+	auto it = rings.find(device);
+	if (it == rings.end())
+		it = rings.emplace(device, std::make_pair(torch::zeros({kPinnedSlots}, torch::dtype(torch::kInt64).pinned_memory(true)), (int64_t)0)).first;
+	return it->second.first.data_ptr<int64_t>() + (it->second.second++ % kPinnedSlots);
+}
+
+// instance capacity to size the binning buffer with before num_rendered has reached the host: 25 % above the (slowly decaying)
+// running maximum of what this problem shape produced so far; -1: no history yet
+std::mutex g_hint_mu;
+std::map<std::tuple<int, int, int, int>, double> g_hint;
+int64_t capacity_guess(int device, int P, int W, int H)
+{
+	std::lock_guard<std::mutex> lock(g_hint_mu);
+	auto it = g_hint.find(std::make_tuple(device, P, W, H));
+	return it == g_hint.end() ? -1 : (int64_t)(it->second * 1.25) + 65536;
+}
+void capacity_update(int device, int P, int W, int H, int64_t R)
+{
+	std::lock_guard<std::mutex> lock(g_hint_mu);
+	double &h = g_hint[std::make_tuple(device, P, W, H)];
+	h = std::max((double)R, 0.98 * h);
 }
 
 Tensor bytes(size_t n, const Tensor &like) { return torch::empty({(int64_t)n}, like.options().dtype(torch::kUInt8)); }
@@ -82,12 +102,14 @@ std::tuple<int64_t, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> rast
 	const int C = has_colors ? (int)colors.size(1) : 3;
 	const int M = sh.numel() != 0 ? (int)sh.size(1) : 0;
 	const auto f32 = means3D.options().dtype(torch::kFloat32);
-	Tensor out_color = torch::zeros({C, H, W}, f32), out_depth = torch::zeros({1, H, W}, f32), out_unc = torch::zeros({1, H, W}, f32);
-	Tensor radii = torch::zeros({P}, means3D.options().dtype(torch::kInt32));
-	if (P == 0) { // rasterize_points.cu:85
+	if (P == 0) { // rasterize_points.cu:85: nothing is launched, the images are the reference's torch::full(0)
 		Tensor e = bytes(0, means3D);
-		return std::make_tuple((int64_t)0, out_color, out_depth, out_unc, radii, e, e.clone(), e.clone());
+		return std::make_tuple((int64_t)0, torch::zeros({C, H, W}, f32), torch::zeros({1, H, W}, f32), torch::zeros({1, H, W}, f32),
+		                       torch::zeros({0}, means3D.options().dtype(torch::kInt32)), e, e.clone(), e.clone());
 	}
+	// every element of the four outputs is written by the kernels (the reference zero-fills them first, rasterize_points.cu:69-72)
+	Tensor out_color = torch::empty({C, H, W}, f32), out_depth = torch::empty({1, H, W}, f32), out_unc = torch::empty({1, H, W}, f32);
+	Tensor radii = torch::empty({P}, means3D.options().dtype(torch::kInt32));
 	TORCH_CHECK_VALUE(means3D.is_cuda(), "means3D must be a CUDA tensor (there is no CPU rasterizer)");
 	const c10::cuda::CUDAGuard guard(means3D.device());
 	const F32 m3(means3D, "means3D"), col(colors, "colors"), op(opacity, "opacity"), un(uncertaintys, "uncertainties"), sc(scales, "scales"),
@@ -99,13 +121,27 @@ std::tuple<int64_t, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> rast
 	check_rc(gsr_forward_stage1(P, C, degree, M, m3.ptr(), shs.ptr(), col.ptr(), op.ptr(), un.ptr(), sc.ptr(), scale_modifier, ro.ptr(),
 	                            cov.ptr(), view.ptr(), proj.ptr(), cam.ptr(), W, H, tan_fovx, tan_fovy, prefiltered ? 1 : 0,
 	                            radii.data_ptr<int>(), geom.data_ptr(), (size_t)geom.numel(), R_host, stream));
-	// the one host sync the reference API imposes: num_rendered is part of the return value and sizes the binning buffer
-	AT_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+	// The reference returns num_rendered and sizes the binning buffer from it: one blocking copy in the middle of the forward
+	// (CR/rasterizer_impl.cu:287).  Here the second half is launched right behind the first with a buffer sized from an estimate
+	// (its kernels read num_rendered from device memory) and the host waits for stage 1's counter only; a wrong estimate costs
+	// one repeat of the second half.
+	at::cuda::CUDAEvent counted;
+	counted.record(at::cuda::getCurrentCUDAStream());
+	auto second_half = [&](int64_t num_rendered, int64_t capacity) {
+		Tensor buf = bytes(gsr_binning_bytes(P, capacity, W, H), means3D);
+		check_rc(gsr_forward_stage2(P, C, num_rendered, col.ptr(), bg.ptr(), W, H, geom.data_ptr(), (size_t)geom.numel(), buf.data_ptr(),
+		                            (size_t)buf.numel(), img.data_ptr(), (size_t)img.numel(), out_color.data_ptr<float>(),
+		                            out_depth.data_ptr<float>(), out_unc.data_ptr<float>(), stream));
+		return buf;
+	};
+	const int dev = (int)means3D.get_device();
+	const int64_t guess = capacity_guess(dev, P, W, H);
+	Tensor binning;
+	if (guess >= 0) binning = second_half(-1, guess);
+	counted.synchronize();
 	const int64_t R = *R_host;
-	Tensor binning = bytes(gsr_binning_bytes(P, R, W, H), means3D);
-	check_rc(gsr_forward_stage2(P, C, R, col.ptr(), bg.ptr(), W, H, geom.data_ptr(), (size_t)geom.numel(), binning.data_ptr(),
-	                            (size_t)binning.numel(), img.data_ptr(), (size_t)img.numel(), out_color.data_ptr<float>(),
-	                            out_depth.data_ptr<float>(), out_unc.data_ptr<float>(), stream));
+	if (guess < 0 || R > gsr_binning_capacity(P, W, H, (size_t)binning.numel())) binning = second_half(R, R);
+	capacity_update(dev, P, W, H, R);
 	if (debug) AT_CUDA_CHECK(cudaDeviceSynchronize()); // CHECK_CUDA(debug), CR/auxiliary.h:166-173
 	return std::make_tuple(R, out_color, out_depth, out_unc, radii, geom, binning, img);
 }

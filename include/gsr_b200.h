@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GSR_API __attribute__((visibility("default")))
@@ -61,6 +61,10 @@ GSR_API const char *gsr_error_string(int code);
 GSR_API size_t gsr_geom_bytes(int P);
 GSR_API size_t gsr_image_bytes(int width, int height);
 GSR_API size_t gsr_binning_bytes(int P, int64_t num_rendered, int width, int height);
+/* The binning buffer describes itself: its layout follows from its size (the largest instance count whose layout fits), so a
+ * buffer may be sized from an ESTIMATE of num_rendered before the exact value has reached the host.  gsr_binning_capacity
+ * returns that count for a buffer of `binning_bytes` bytes (0: too small for anything). */
+GSR_API int64_t gsr_binning_capacity(int P, int width, int height, size_t binning_bytes);
 
 /*
  * Forward, first half — replaces the part of Rasterizer::forward before the blocking
@@ -90,6 +94,13 @@ GSR_API int gsr_forward_stage1(
  * emission (duplicateWithKeys :70-111), stable sort (:309-314), identifyTileRanges (:116-138)
  * and the blend kernel renderCUDA (CR/forward.cu:441-568).
  *   background[C]; out_color[C,H,W]; out_depth[1,H,W]; out_uncertainty[1,H,W]
+ * No host round trip is needed between the two halves: the kernels read num_rendered from device memory (stage 1 left it in
+ * geom_buffer) and take their grids from the capacity of `binning_buffer` (gsr_binning_capacity).
+ *   num_rendered >= 0: the exact value, if the caller already has it (checked against the capacity: GSR_E_WORKSPACE);
+ *   num_rendered == -1: not known yet.  The caller launches this call right behind stage 1 with a buffer sized from an
+ *                  estimate, then waits for stage 1's pinned counter only; if the counter exceeds gsr_binning_capacity() the
+ *                  call has rendered nothing but the background (every tile range empty, no out-of-bounds access) and is
+ *                  simply repeated with a large enough buffer.
  */
 GSR_API int gsr_forward_stage2(
     int P, int C, int64_t num_rendered,
@@ -291,7 +302,7 @@ GSR_API int gsr_adam_step(int n_tensors, const gsr_adam_tensor *tensors_host, gs
  */
 GSR_API int gsr_debug_export(
     int P, int64_t num_rendered, int width, int height,
-    const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
+    const void *geom_buffer, const void *binning_buffer, size_t binning_bytes, const void *image_buffer,
     float *xy, float *depths, float *conic_opacity, uint32_t *tiles_touched,
     uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib,
     gsr_stream_t stream);

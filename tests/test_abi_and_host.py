@@ -40,7 +40,7 @@ def test_library_is_sm100a_only():
 
 
 def test_capability_and_size_queries(lib):
-    assert lib.gsr_abi_version() == 1
+    assert lib.gsr_abi_version() == 2
     assert lib.gsr_supported_channels(3) == 1 and lib.gsr_supported_channels(32) == 1
     assert lib.gsr_supported_channels(5) == 0
     g1, g2 = lib.gsr_geom_bytes(1000), lib.gsr_geom_bytes(2000)
