@@ -79,6 +79,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the `ncu --set full` capture recorded in
+    profiles/traffic.json — valid only for the library build it was captured from (keyed by the build digest of the sources +
+    flags, gscream_b200/_build.py); any other build reports null rather than a stale constant."""
+    try:
+        from gscream_b200 import _build
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            table = json.load(fh)
+        entry = table.get(_build._digest(), {}).get(kernel)
+        return (int(entry["dram_bytes"]), entry.get("source")) if entry else (None, None)
+    except Exception:
+        return None, None
+
+
 def _dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,6 +201,12 @@ def run_ours(args, cfg, rank, world, local):
         n = lib.gsr_profile_read(sid, buf.ctypes.data, 256)
         stage_ms[name] = float(buf[:n].mean()) if n > 0 else None
     lib.gsr_profile_enable(0)
+    stage_ms_rank0 = dict(stage_ms)
+    if world > 1:   # ms_per_step is the max over ranks; so are the stage times (rank 0's own are kept beside them)
+        names = sorted(stage_ms)
+        t = torch.tensor([stage_ms[k] or 0.0 for k in names], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stage_ms = {k: float(v) for k, v in zip(names, t.tolist())}
     ms_per_step = ms / args.steps
     value = world * 1000.0 / ms_per_step
     R = int(info["R"])
@@ -304,6 +324,26 @@ def run_ours(args, cfg, rank, world, local):
     e2e_value = world * 1000.0 * args.steps / e2e_ms
     del vslots, res, m2d_res
 
+    # ---- public API + autograd with everything resident on the device: the like-for-like arm against `--impl reference`
+    # (which is timed exactly this way) ----
+    res = {k: scene[k].clone().requires_grad_(True) for k in keys}
+    m2d_res = torch.zeros_like(res["means3D"], requires_grad=True)
+    st_res = ours.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], scene["bg"], 1.0, cam["viewmatrix"], cam["projmatrix"],
+                                                1, cam["campos"], False, False)
+    rast_res = ours.GaussianRasterizer(st_res)
+
+    def api_step():
+        color, depth, unc, radii = rast_res(means3D=res["means3D"], means2D=m2d_res, opacities=res["opacities"], uncertainties=res["uncertainties"],
+                                            shs=None, colors_precomp=res["colors"], scales=res["scales"], rotations=res["rotations"], cov3D_precomp=None)
+        torch.autograd.backward((color, depth, unc), ups[0])
+        for t in list(res.values()) + [m2d_res]:
+            t.grad = None
+
+    api_ms, _ = _timed(api_step, args.steps, max(3, args.warmup), world)
+    torch.cuda.synchronize()
+    api_value = world * 1000.0 * args.steps / api_ms
+    del res, m2d_res
+
     # per-tile list length statistics (outside any timed region)
     from gscream_b200 import _C as gC
     outs = render_views_into_bucket(scene, [cam], ups, bucket.zero_(), keep_outputs=False)
@@ -320,7 +360,9 @@ def run_ours(args, cfg, rank, world, local):
     if rank == 0:
         peak, peak_src = _peaks()
         bytes_bwd = algorithmic_bytes_blend_backward(C, W, H, R, V)
-        t_bwd = stage_ms["blend_backward"]
+        t_bwd = stage_ms_rank0["blend_backward"]
+        bwd_kernel = "gsr::blend_backward_c32_kernel" if C == 32 else "gsr::blend_backward_kernel<%d>" % C
+        traffic, traffic_src = _measured_traffic(bwd_kernel + ":" + args.workload) if args.scale_mult == 1.0 else (None, None)
         achieved = bytes_bwd / (t_bwd * 1e-3) / 1e9 if t_bwd else None
         out = {
             "metric": "fwd+bwd views/sec", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -333,23 +375,56 @@ def run_ours(args, cfg, rank, world, local):
                        "l2": "working set (features 128 MB + records 64 MB + planes 282 MB x2) exceeds the 126 MB L2; no explicit flush",
                        "collective": "1 NCCL sum-allreduce of the %.0f MB gradient bucket per step" % (bucket.nbytes() / 1e6) if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d_view_bytes, "d2h_bytes_per_step": 4,
-                    "note": "public GaussianRasterizer API + autograd; per step the camera and the view's upstream-gradient planes (C colour + depth + uncertainty) are copied from pinned host memory (double-buffered on a copy stream), the Gaussian arrays are resident like model weights, a result scalar is read back"},
+                    "note": "public GaussianRasterizer API + autograd; per step the camera and the view's upstream-gradient planes (C colour + depth + uncertainty) are copied from pinned host memory (double-buffered on a copy stream), the Gaussian arrays are resident like model weights. Device -> host: ONE scalar (4 bytes) — the rendered planes are NOT copied back, their consumer (the loss) lives on the device as in GScream (scene/cameras.py keeps the images on the GPU). At config3 the 282 MB of upload per step make this number a measurement of the PCIe link, not of the kernels"},
+            "e2e_device_resident_api": {"value": api_value, "unit": "views/s", "ms_per_step": api_ms / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "public GaussianRasterizer API + torch.autograd.backward with every tensor resident on the device: the like-for-like arm against `--impl reference`, which is timed exactly this way (its `value`)"},
             "e2e_all_inputs_from_host": {"value": e2e_all_value, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "note": "strictest form: ALL Gaussian arrays, camera and upstream gradient planes copied from pinned host memory every step; PCIe-bound"},
             "gpu_launches": launches, "clocks": clocks,
-            "stage_ms": stage_ms,
-            "roofline": {"bound": "hbm", "kernel": "gsr::blend_backward_kernel<%d>" % C, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "stage_ms": stage_ms, "stage_ms_note": "per-stage CUDA-event means inside the timed region; max over ranks" if world > 1 else "per-stage CUDA-event means inside the timed region",
+            "roofline": {"bound": "hbm", "kernel": bwd_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of this
-                         # workload (profiles/r1_blend_v7_summary.md: 392.95 MB + 27.03 MB); config3 only
-                         "traffic": 419970304 if (args.workload == "config3" and args.scale_mult == 1.0) else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the `ncu --set full` capture recorded
+                         # for THIS build of the library (profiles/traffic.json, keyed by the build digest); null for any other build
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_bwd,
                          "avg_launch_ms": t_bwd, "peak_source": peak_src,
-                         "note": "blend kernels are FP32-issue bound, not HBM bound (see DESIGN.md / profiles/)"},
+                         "note": "the blend kernels are issue / tensor-pipe bound, not HBM bound: their DRAM traffic is a quarter of the algorithmic bytes (L2 absorbs the re-gathers), see DESIGN.md section 4 and profiles/r2_*"},
         }
+        if world > 1:
+            out["stage_ms_rank0"] = stage_ms_rank0
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_port(cfg)
     return out
+
+
+def other_configs():
+    """The other BASELINE.json configurations, measured by this same run so that they are driver-run numbers too: config2
+    (configs[1]) and the config4 substitute (configs[3]), each with both arms.  One child process per arm; device
+    timed like the main line; a few seconds each."""
+    res = {}
+    for wl, steps in (("config2", 40), ("config4", 20)):
+        for impl in ("ours", "reference"):
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--impl", impl, "--steps", str(steps), "--warmup", "5",
+                   "--no-cpu-baseline", "--no-other-configs"]
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                if "unavailable" in d:
+                    res.setdefault(wl, {})[impl] = {"unavailable": d["unavailable"]}
+                    continue
+                e = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "workload": d["config"]["workload"]}
+                if "stage_ms" in d:
+                    e["stage_ms"] = d["stage_ms"]
+                if "e2e_device_resident_api" in d:
+                    e["device_resident_api"] = d["e2e_device_resident_api"]["value"]
+                res.setdefault(wl, {})[impl] = e
+            except Exception as ex:  # a failed extra must not lose the main line
+                res.setdefault(wl, {})[impl] = {"error": repr(ex)[:200]}
+        a, b = res[wl].get("ours", {}), res[wl].get("reference", {})
+        if "value" in a and "value" in b:
+            res[wl]["ratio"] = a["value"] / b["value"]
+    return res
 
 
 def run_reference(args, cfg, rank, world, local):
@@ -506,6 +581,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=["config2", "config3", "config4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config2 / config4 arms that the default 1-GPU run appends")
     ap.add_argument("--scale-mult", type=float, default=1.0,
                     help="multiply the synthetic splat scale (SURVEY 8d 'heavy' variant: 3.0); 1.0 is the BASELINE.json workload")
     args = ap.parse_args()
@@ -531,6 +607,9 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     out = run_ours(args, cfg, rank, world, local)
+    if rank == 0 and world == 1 and args.workload == "config3" and args.scale_mult == 1.0 and not args.no_other_configs:
+        torch.cuda.empty_cache()
+        out["other_configs"] = other_configs()
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -429,7 +429,7 @@ int gsr_training_statis(int A, int n_offsets, int64_t n_vis, int64_t P, const ui
 		return GSR_E_BADARG;
 	if (P > 0 && (!update_filter || !viewspace_grad)) return GSR_E_BADARG;
 	if (scratch_bytes < statis_scratch_bytes(A, n_offsets) || !aligned16(scratch)) return GSR_E_WORKSPACE;
-	GSR_CUDA(training_statis(A, n_offsets, n_vis, anchor_visible_mask, offset_selection_mask, update_filter, neural_opacity, viewspace_grad,
+	GSR_CUDA(training_statis(A, n_offsets, n_vis, P, anchor_visible_mask, offset_selection_mask, update_filter, neural_opacity, viewspace_grad,
 	                         opacity_accum, anchor_demon, offset_gradient_accum, offset_denom, (char *)scratch, stream));
 	return 0;
 }

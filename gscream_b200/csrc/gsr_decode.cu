@@ -541,7 +541,10 @@ __global__ void __launch_bounds__(256, 2) decode_backward_kernel(DecodeBwdArgs a
 //   opacity_accum[a]            += sum_j max(neural_opacity[r, j], 0)           for visible anchors (r = visible rank)
 //   anchor_demon[a]             += 1
 //   offset_gradient_accum[a, j] += |viewspace_grad[p, :2]|,  offset_denom[a, j] += 1   for selected offsets whose Gaussian p has radii > 0
-__global__ void __launch_bounds__(256) training_statis_kernel(int A, int k, const uint8_t *__restrict__ anchor_visible, const uint32_t *__restrict__ vis_incl,
+// n_vis / P: row counts of neural_opacity (n_vis * k) and of update_filter / viewspace_grad.  A mask whose popcount disagrees with
+// them (the reference raises a shape mismatch from its boolean-mask assignment there) must not index out of bounds: such rows
+// are skipped.
+__global__ void __launch_bounds__(256) training_statis_kernel(int A, int k, int64_t n_vis, int64_t P, const uint8_t *__restrict__ anchor_visible, const uint32_t *__restrict__ vis_incl,
                                                               const uint8_t *__restrict__ offset_selected, const uint32_t *__restrict__ sel_incl,
                                                               const uint8_t *__restrict__ update_filter, const float *__restrict__ neural_opacity,
                                                               const float *__restrict__ viewspace_grad, float *__restrict__ opacity_accum,
@@ -551,6 +554,7 @@ __global__ void __launch_bounds__(256) training_statis_kernel(int A, int k, cons
 	const int a = blockIdx.x * blockDim.x + threadIdx.x;
 	if (a >= A || !anchor_visible[a]) return;
 	const size_t r = (size_t)vis_incl[a] - 1;
+	if ((int64_t)r >= n_vis) return;
 	float osum = 0.f;
 	for (int j = 0; j < k; j++) {
 		const size_t t = r * k + j;
@@ -558,6 +562,7 @@ __global__ void __launch_bounds__(256) training_statis_kernel(int A, int k, cons
 		osum += o < 0.f ? 0.f : o;
 		if (offset_selected[t]) {
 			const size_t p = (size_t)sel_incl[t] - 1;
+			if ((int64_t)p >= P) continue;
 			if (update_filter[p]) {
 				const float gx = viewspace_grad[p * 3 + 0], gy = viewspace_grad[p * 3 + 1];
 				offset_gradient_accum[(size_t)a * k + j] += sqrtf(gx * gx + gy * gy);
@@ -683,7 +688,7 @@ size_t statis_scratch_bytes(int A, int k)
 	return 2 * align_up(a * 4) + 2 * align_up(n * 4) + scan_scratch_bytes((int64_t)n);
 }
 
-cudaError_t training_statis(int A, int k, int64_t n_vis, const uint8_t *anchor_visible, const uint8_t *offset_selected, const uint8_t *update_filter,
+cudaError_t training_statis(int A, int k, int64_t n_vis, int64_t P, const uint8_t *anchor_visible, const uint8_t *offset_selected, const uint8_t *update_filter,
                             const float *neural_opacity, const float *viewspace_grad, float *opacity_accum, float *anchor_demon,
                             float *offset_gradient_accum, float *offset_denom, char *scratch, cudaStream_t stream)
 {
@@ -700,7 +705,7 @@ cudaError_t training_statis(int A, int k, int64_t n_vis, const uint8_t *anchor_v
 		if ((e = inclusive_sum_gather(sflag, nullptr, sincl, (int64_t)n, tmp, stream)) != cudaSuccess) return e;
 		count_launch();
 	}
-	training_statis_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, k, anchor_visible, vincl, offset_selected, sincl, update_filter, neural_opacity,
+	training_statis_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, k, n_vis, P, anchor_visible, vincl, offset_selected, sincl, update_filter, neural_opacity,
 	                                                          viewspace_grad, opacity_accum, anchor_demon, offset_gradient_accum, offset_denom);
 	count_launch();
 	return cudaGetLastError();

@@ -50,7 +50,7 @@ cudaError_t decode_backward(const DecodeBwdArgs &a, cudaStream_t stream);
 
 // densification statistics (GaussianModel.training_statis)
 size_t statis_scratch_bytes(int A, int k);
-cudaError_t training_statis(int A, int k, int64_t n_vis, const uint8_t *anchor_visible, const uint8_t *offset_selected, const uint8_t *update_filter,
+cudaError_t training_statis(int A, int k, int64_t n_vis, int64_t P, const uint8_t *anchor_visible, const uint8_t *offset_selected, const uint8_t *update_filter,
                             const float *neural_opacity, const float *viewspace_grad, float *opacity_accum, float *anchor_demon,
                             float *offset_gradient_accum, float *offset_denom, char *scratch, cudaStream_t stream);
 

@@ -79,11 +79,12 @@ __global__ void __launch_bounds__(kAdamThreads) adam_step_kernel(const __grid_co
 
 cudaError_t launch_adam_step(int n_tensors, const AdamTensor *tensors, cudaStream_t stream)
 {
-	for (int first = 0; first < n_tensors; first += kAdamMaxTensors) {
+	for (int first = 0; first < n_tensors;) {
 		AdamTable tab;
 		tab.n = 0;
 		int blocks = 0;
-		for (int k = first; k < n_tensors && tab.n < kAdamMaxTensors; k++) {
+		int k = first;
+		for (; k < n_tensors && tab.n < kAdamMaxTensors; k++) {
 			if (tensors[k].n <= 0) continue;
 			const int64_t nb = (tensors[k].n + kAdamChunk - 1) / kAdamChunk;
 			if (nb > (int64_t)0x7fffffff - blocks) return cudaErrorInvalidValue;
@@ -92,6 +93,7 @@ cudaError_t launch_adam_step(int n_tensors, const AdamTensor *tensors, cudaStrea
 			tab.block_end[tab.n] = blocks;
 			tab.n++;
 		}
+		first = k; // (not first + kAdamMaxTensors: skipped empty descriptors do not count against the table)
 		if (tab.n == 0) continue;
 		adam_step_kernel<<<blocks, kAdamThreads, 0, stream>>>(tab);
 		count_launch();

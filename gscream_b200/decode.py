@@ -7,19 +7,28 @@ include/gsr_b200.h).  Torch owns the memory, names the stream and provides the a
 eager-torch fallback: unsupported configurations (use_feat_bank, feat_dim != 32, n_offsets > 16) raise.
 """
 import ctypes
+import itertools
+import threading
 
 import torch
 
 from . import _lib
 
 _PINNED = {}
+_PINNED_LOCK = threading.Lock()
+_PINNED_SLOTS = 64
 
 
 def _pinned_counts(device):
+    """Two pinned int64 (n_vis, P) for one call: slots rotate through a small per-device ring so that concurrent calls on one
+    device never share counters (a call reads its own values before it returns)."""
     key = device.index if device.index is not None else torch.cuda.current_device()
-    if key not in _PINNED:
-        _PINNED[key] = torch.zeros(2, dtype=torch.int64).pin_memory()
-    return _PINNED[key]
+    with _PINNED_LOCK:
+        if key not in _PINNED:
+            _PINNED[key] = (torch.zeros(2 * _PINNED_SLOTS, dtype=torch.int64).pin_memory(), itertools.count())
+        ring, counter = _PINNED[key]
+        i = 2 * (next(counter) % _PINNED_SLOTS)
+        return ring[i:i + 2]
 
 
 def _stream():

@@ -20,6 +20,34 @@ from gscream_b200 import rasterizer as ours
 
 pytestmark = pytest.mark.gpu
 REL = 1e-5
+# SURVEY 8d's gate as written is per element, |new - ref| <= 1e-5 max(|ref|, eps_plane).  The absolute checks below use
+# eps_plane = max|ref| (the plane's scale); next to them every comparison also reports the per-element RELATIVE error with the
+# floor eps = REL_FLOOR * max|ref| and asserts the bound stated here.  Planes meet 1e-5-class bounds; gradients are sums of
+# thousands of atomically accumulated terms, where the reference itself moves by REL_FLOOR-relative amounts between two of its
+# own runs on small elements, so their bound is the looser of the two and the reference's own run-to-run figure is reported
+# beside ours (GSR_PARITY_REPORT=<file> appends one JSON line per comparison).
+REL_FLOOR = 1e-3
+# measured on B200 (profiles/r2_parity.md): depth / uncertainty planes 3.5e-7; colour planes 3e-7 at C = 3 and 2.8e-4 at C = 32,
+# where the accumulation runs as 3xTF32 on the tensor pipe (~7e-7 of sum |w f| per pixel, which this metric divides by values
+# as small as 1e-3 of the plane's scale)
+REL_BOUND_PLANES = 1e-3
+REL_BOUND_GRADS = 2e-2
+ARBITER_HITS = []   # (tensor, err, tol): comparisons that were settled by the fp64 oracle instead of the tolerance
+
+
+def _rel_floor(a, ref):
+    floor = REL_FLOOR * float(np.abs(ref).max())
+    if floor == 0.0:
+        return 0.0
+    return float((np.abs(a - ref) / np.maximum(np.abs(ref), floor)).max())
+
+
+def _report(tag, k, ours_rel, ref_rel=None, bound=None):
+    import json, os
+    path = os.environ.get("GSR_PARITY_REPORT")
+    if path:
+        with open(path, "a") as fh:
+            fh.write(json.dumps(dict(case=tag, tensor=k, rel_err_floor1e3=ours_rel, reference_rerun_rel=ref_rel, bound=bound)) + "\n")
 
 
 def _require_native():
@@ -55,23 +83,36 @@ def _check_ints_and_projection(m, e, ref_radii, ref_geom, ref_img, ref_plist, R)
     assert np.array_equal(e["final_T"].view(np.uint32), ref_img["final_T"].view(np.uint32))  # same alpha chain, bit for bit
 
 
-def _check_floats(m, ref, spread=None, truth=None):
-    """`truth` (optional, fp64 oracle gradients): arbiter for ill-conditioned cases where the reference's own atomic-order
-    jitter is of the order of the tolerance and two or four of its runs under-estimate it — a tensor that misses the
-    reference by more than the tolerance still passes if it is at least as close to the fp64 result as the reference is."""
+def _check_floats(m, ref, spread=None, truth=None, rerun=None, tag=""):
+    """`truth` (optional, fp64 oracle gradients; adversarial cases only): arbiter for ill-conditioned cases where the
+    reference's own atomic-order jitter is of the order of the tolerance and two or four of its runs under-estimate it — a
+    tensor that misses the reference by more than the tolerance still passes if it is at least as close to the fp64 result as
+    the reference is.  Every use is recorded in ARBITER_HITS and bounded by test_zz_arbiter_usage.
+    `rerun`: a second run of the reference (its own run-to-run relative figure is reported next to ours)."""
     for k in ("color", "depth", "uncertainty"):
         tol = REL * np.abs(ref[k]).max()
         assert np.abs(m[k] - ref[k]).max() <= tol, (k, float(np.abs(m[k] - ref[k]).max()), float(tol))
+        r = _rel_floor(m[k], ref[k])
+        _report(tag, k, r, None, REL_BOUND_PLANES)
+        assert r <= REL_BOUND_PLANES, (k, "per-element relative error (floor %g x max)" % REL_FLOOR, r)
     for k in GRAD_KEYS:
         rel = REL if k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_duncertainty") else 3 * REL
         tol = rel * np.abs(ref[k]).max() + (8.0 * spread[k] if spread else 0.0)
         err = float(np.abs(m[k] - ref[k]).max())
+        arbitrated = False
         if err > tol and truth is not None and k in truth:
             t = truth[k].reshape(ref[k].shape)
             ours_off, ref_off = float(np.abs(m[k] - t).max()), float(np.abs(ref[k] - t).max())
             assert ours_off <= ref_off + rel * np.abs(ref[k]).max(), (k, "vs fp64 oracle: ours %.3e, reference %.3e" % (ours_off, ref_off), err, float(tol))
+            ARBITER_HITS.append((tag, k, err, float(tol)))
+            arbitrated = True
         else:
             assert err <= tol, (k, err, float(tol))
+        r = _rel_floor(m[k], ref[k])
+        r_ref = _rel_floor(rerun[k], ref[k]) if rerun is not None else None
+        _report(tag, k, r, r_ref, REL_BOUND_GRADS)
+        if not arbitrated:
+            assert r <= max(REL_BOUND_GRADS, 8.0 * (r_ref or 0.0)), (k, "per-element relative error (floor %g x max)" % REL_FLOOR, r, r_ref)
         assert not m[k][ref["radii"] == 0].any()  # culled Gaussians: exactly zero
 
 
@@ -89,7 +130,7 @@ def test_against_reference_golden(name):
     _check_ints_and_projection(m, e, g["radii"], geom, img, g["bin_point_list"], int(g["num_rendered"]))
     ref = {k: g[k] for k in ["color", "depth", "uncertainty", "radii"] + GRAD_KEYS}
     spread = {k: float(np.abs(g["rerun_" + k] - g[k]).max()) for k in GRAD_KEYS}
-    _check_floats(m, ref, spread)
+    _check_floats(m, ref, spread, rerun={k: g["rerun_" + k] for k in GRAD_KEYS}, tag="golden:" + name)
 
 
 # ---- (2) CPU oracle on fresh inputs and edge cases ------------------------------------------------------------
@@ -323,7 +364,7 @@ def test_full_size_against_reference_build(cfg, smult):
     e = _export(m, P, W, H)
     _check_ints_and_projection(m, e, r["radii"], geom, img, binn["point_list"], R)
     spread = {k: float(np.abs(r2[k] - r[k]).max()) for k in GRAD_KEYS}
-    _check_floats(m, r, spread)
+    _check_floats(m, r, spread, rerun=r2, tag="full:%s:x%g" % (cfg, smult))
 
 
 def _compare_with_reference_build(scene, cam, grads, C, ref_runs=2, oracle_arbiter=False):
@@ -340,7 +381,7 @@ def _compare_with_reference_build(scene, cam, grads, C, ref_runs=2, oracle_arbit
     _check_ints_and_projection(m, e, r["radii"], geom, img, binn["point_list"], R)
     spread = {k: max(float(np.abs(r2[k] - r[k]).max()) for r2 in reruns) for k in GRAD_KEYS}
     truth = _oracle_run(scene, cam, grads, "f64")[1] if oracle_arbiter else None
-    _check_floats(m, r, spread, truth)
+    _check_floats(m, r, spread, truth, rerun=reruns[0], tag="refbuild:P%d:%dx%d:C%d%s" % (P, W, H, C, ":adversarial" if oracle_arbiter else ""))
     return r
 
 
@@ -401,7 +442,7 @@ def test_plain_point_list_fallback_matches_golden(name):
     _check_ints_and_projection(m, e, g["radii"], geom, img, g["bin_point_list"], int(g["num_rendered"]))
     ref = {k: g[k] for k in ["color", "depth", "uncertainty", "radii"] + GRAD_KEYS}
     spread = {k: float(np.abs(g["rerun_" + k] - g[k]).max()) for k in GRAD_KEYS}
-    _check_floats(m, ref, spread)
+    _check_floats(m, ref, spread, rerun={k: g["rerun_" + k] for k in GRAD_KEYS}, tag="plain:" + name)
 
 
 # ---- (4) size-independent properties at full size --------------------------------------------------------------
@@ -449,3 +490,39 @@ def test_properties_at_full_size():
         got = bucket.views[name].cpu().numpy()
         tol = 3 * REL * np.abs(cs[k]).max()
         assert np.abs(got - (a[k] + c2[k])).max() <= tol, k
+
+
+def test_binning_estimate_too_small_repeats_the_second_half():
+    """The forward launches its second half with a binning buffer sized from an estimate of num_rendered (gscream_b200/_C.py);
+    when the estimate is too small the call must notice and repeat that half with the exact size: same results to the bit."""
+    _require_native()
+    P, W, H, C = 20000, 320, 200, 32
+    sc = scenes.make_scene(P, W, H, C, 1234, scale_mult=2.0)
+    cam = scenes.make_camera(W, H)
+    grads = scenes.make_upstream_grads(C, W, H, 1234)
+    a = ru.run_impl(ours, sc, cam, grads)            # first call of this shape: exact path (no history)
+    key = (torch.cuda.current_device(), P, W, H)
+    assert _C._R_HINT[key] >= a["num_rendered"]
+    b = ru.run_impl(ours, sc, cam, grads)            # estimate path, large enough
+    _C._R_HINT[key] = 1.0                            # force an estimate far below num_rendered
+    c = ru.run_impl(ours, sc, cam, grads)
+    lib = _lib.load()
+    for r in (b, c):
+        assert r["num_rendered"] == a["num_rendered"]
+        assert lib.gsr_binning_capacity(P, W, H, r["_binning"].numel()) >= a["num_rendered"]
+        for k in ("color", "depth", "uncertainty", "radii"):
+            assert np.array_equal(a[k], r[k]), k
+        ea, er = _export(a, P, W, H), _export(r, P, W, H)
+        assert np.array_equal(ea["point_list"], er["point_list"]) and np.array_equal(ea["ranges"], er["ranges"])
+        for k in GRAD_KEYS:
+            assert np.abs(a[k] - r[k]).max() <= 3 * REL * np.abs(a[k]).max(), k
+    assert _C._R_HINT[key] >= a["num_rendered"]      # the history recovered
+
+
+def test_zz_arbiter_usage():
+    """Runs last in this module: the fp64-oracle arbiter may only have settled comparisons of the adversarial cases, and only
+    for the tensors behind the ill-conditioned cov2D -> cov3D -> scale / rotation chain."""
+    for tag, k, err, tol in ARBITER_HITS:
+        assert tag.endswith(":adversarial"), (tag, k, err, tol)
+        assert k in ("dL_dscales", "dL_drotations", "dL_dmeans3D"), (tag, k, err, tol)
+    assert len(ARBITER_HITS) <= 4, ARBITER_HITS
