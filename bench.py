@@ -172,6 +172,8 @@ def run_ours(args, cfg, rank, world, local):
     P, W, H, C, seed = cfg["P"], cfg["W"], cfg["H"], cfg["C"], cfg["seed"]
     scene_cpu = scenes.make_scene(P, W, H, C, seed, scale_mult=args.scale_mult)  # identical bits on every rank
     yaw = (rank - (world - 1) / 2.0) * 3.0                                # every rank renders its own view
+    if args.yaw_deg is not None:
+        yaw = args.yaw_deg
     cam_cpu = scenes.make_camera(W, H, yaw_deg=yaw)
     grads_cpu = scenes.make_upstream_grads(C, W, H, seed + rank)
     scene = {k: v.to(dev) for k, v in scene_cpu.items()}
@@ -212,6 +214,11 @@ def run_ours(args, cfg, rank, world, local):
     R = int(info["R"])
     V = int((info["radii"] > 0).sum().item())
 
+    if args.value_only:
+        if rank == 0:
+            return {"metric": "fwd+bwd views/sec", "value": value, "unit": "views/s", "n_gpus": world, "ms_per_step": ms_per_step, "num_rendered": R, "visible": V,
+                    "stage_ms": stage_ms, "stage_ms_rank0": stage_ms_rank0, "note": "--value-only development run"}
+        return None
     # ---- end to end through the public API, inputs from pinned host memory every step ----
     keys = ("means3D", "colors", "opacities", "uncertainties", "scales", "rotations")
     host = {k: scene_cpu[k].pin_memory() for k in keys}
@@ -581,6 +588,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=["config2", "config3", "config4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--yaw-deg", type=float, default=None, help="development aid: camera yaw of this rank's view (default: 3 degrees x (rank - (N-1)/2))")
+    ap.add_argument("--value-only", action="store_true", help="development aid: skip the end-to-end arms (the printed line then lacks them)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the config2 / config4 arms that the default 1-GPU run appends")
     ap.add_argument("--scale-mult", type=float, default=1.0,
                     help="multiply the synthetic splat scale (SURVEY 8d 'heavy' variant: 3.0); 1.0 is the BASELINE.json workload")

@@ -112,10 +112,29 @@ BinningLayout binning_layout(int P, int64_t R, int W, int H)
 // in cost (77 -> 139 us) once the per-instance warp mask was added.
 // The value carries, above the 24-bit Gaussian id, the 8-bit mask of the tile's warps whose 8x4 pixel block the Gaussian's
 // alpha >= 1/255 bounding box touches (gsr_blend.cuh).
+// A Gaussian covering more than kBigRect tiles (a splat close to the camera plane can cover the whole grid: thousands of
+// instances) is not emitted by its warp — 32 such neighbours in the depth order would serialise 10^5 instances in one warp
+// (measured: the stage tripled, 0.25 -> 0.75 ms, on views with a few dozen of them, profiles/r2_binning.md) — but queued for
+// emit_big_kernel, which spreads each of them over a whole CTA.
+constexpr uint32_t kBigRect = 256;
+
+__device__ __forceinline__ void emit_one(uint32_t g, int e, int x0, int y0, int w, float cx, float cy, float hx, float hy, int gx, bool packed,
+                                         uint32_t *__restrict__ key, uint32_t *__restrict__ val)
+{
+	// entry e of the rectangle in row-major order (y outer, x inner), as duplicateWithKeys emits it
+	const int ry = e / w, rx = e - ry * w;
+	const int tx = x0 + rx, ty = y0 + ry;
+	uint32_t v = g;
+	if (packed) v |= warp_overlap_mask(cx, cy, hx, hy, (float)(tx * GSR_BLOCK_X), (float)(ty * GSR_BLOCK_Y)) << 24;
+	*key = (uint32_t)(ty * gx + tx);
+	*val = v;
+}
+
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t *__restrict__ order,
                                                              const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ tiles_touched,
                                                              const float *__restrict__ rec, int gx, int gy, bool packed, int64_t capacity,
-                                                             uint32_t *__restrict__ header, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+                                                             uint32_t *__restrict__ header, uint32_t *__restrict__ big_list,
+                                                             uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
 	const int lane = threadIdx.x & 31;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,25 +145,31 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 		header[kHdrOverflow] = (int64_t)R > capacity ? 1u : 0u;
 	}
 	if ((int64_t)R > capacity) return; // the caller sized the buffer from a guess that was too small: it re-runs this stage
-	uint32_t g = 0, tt = 0, incl = 0;
+	uint32_t g = 0, tt = 0, start = 0;
 	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
 	float2 xy = {0.f, 0.f}, ext = {-1.f, -1.f};
 	if (i < P) {
 		g = order[i];
 		tt = tiles_touched[g];
-		incl = offsets[i]; // inclusive scan of tiles_touched in depth order
-		if (tt != 0) {
+		start = offsets[i] - tt; // offsets: inclusive scan of tiles_touched in depth order
+		if (tt > kBigRect) {
+			big_list[atomicAdd(header + kHdrBigCount, 1u)] = (uint32_t)i;
+			tt = 0;
+		} else if (tt != 0) {
 			xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
 			ext = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS + 8);
 			const int radius = (int)rec[(size_t)g * GSR_REC_FLOATS + 13];
 			get_rect(xy.x, xy.y, radius, gx, gy, x0, y0, x1, y1); // same rect as the forward (CR/rasterizer_impl.cu:92)
 		}
 	}
-	// the warp's run of the output: [run_start, run_start + total)
-	const uint32_t run_start = __shfl_sync(0xffffffffu, incl - tt, 0);
-	const int last = min(31, P - 1 - (i - lane));                 // last lane of this warp that maps to a Gaussian
-	const uint32_t total = __shfl_sync(0xffffffffu, incl, last < 0 ? 0 : last) - run_start;
-	const uint32_t end_rel = (i < P) ? incl - run_start : total; // exclusive end of this lane's instances within the run
+	// the warp's instances, numbered 0 .. total-1 through an inclusive scan of the lanes' counts
+	uint32_t end_rel = tt;
+#pragma unroll
+	for (int s = 1; s < 32; s <<= 1) {
+		const uint32_t o = __shfl_up_sync(0xffffffffu, end_rel, s);
+		if (lane >= s) end_rel += o;
+	}
+	const uint32_t total = __shfl_sync(0xffffffffu, end_rel, 31);
 	const int w = x1 - x0;
 	for (uint32_t kb = 0; kb < total; kb += 32) {
 		const uint32_t k = kb + lane;
@@ -157,20 +182,34 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 		}
 		const int src = min(lo, 31);
 		const uint32_t s_g = __shfl_sync(0xffffffffu, g, src), s_tt = __shfl_sync(0xffffffffu, tt, src);
-		const uint32_t s_end = __shfl_sync(0xffffffffu, end_rel, src);
+		const uint32_t s_end = __shfl_sync(0xffffffffu, end_rel, src), s_start = __shfl_sync(0xffffffffu, start, src);
 		const int s_x0 = __shfl_sync(0xffffffffu, x0, src), s_y0 = __shfl_sync(0xffffffffu, y0, src), s_w = __shfl_sync(0xffffffffu, w, src);
 		const float s_cx = __shfl_sync(0xffffffffu, xy.x, src), s_cy = __shfl_sync(0xffffffffu, xy.y, src);
 		const float s_hx = __shfl_sync(0xffffffffu, ext.x, src), s_hy = __shfl_sync(0xffffffffu, ext.y, src);
 		if (k < total) {
-			// entry e of the rectangle in row-major order (y outer, x inner), as duplicateWithKeys emits it
 			const int e = (int)(k - (s_end - s_tt));
-			const int ry = e / s_w, rx = e - ry * s_w;
-			const int tx = s_x0 + rx, ty = s_y0 + ry;
-			uint32_t v = s_g;
-			if (packed) v |= warp_overlap_mask(s_cx, s_cy, s_hx, s_hy, (float)(tx * GSR_BLOCK_X), (float)(ty * GSR_BLOCK_Y)) << 24;
-			keys[run_start + k] = (uint32_t)(ty * gx + tx);
-			vals[run_start + k] = v;
+			emit_one(s_g, e, s_x0, s_y0, s_w, s_cx, s_cy, s_hx, s_hy, gx, packed, keys + s_start + e, vals + s_start + e);
 		}
+	}
+}
+
+// the queued large rectangles: one CTA per Gaussian (round robin over a fixed grid), one thread per instance
+__global__ void __launch_bounds__(256) emit_big_kernel(int P, const uint32_t *__restrict__ order, const uint32_t *__restrict__ offsets,
+                                                       const uint32_t *__restrict__ tiles_touched, const float *__restrict__ rec, int gx, int gy,
+                                                       bool packed, int64_t capacity, const uint32_t *__restrict__ header,
+                                                       const uint32_t *__restrict__ big_list, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+	if ((int64_t)__ldg(offsets + (P - 1)) > capacity) return;
+	const uint32_t count = header[kHdrBigCount];
+	for (uint32_t b = blockIdx.x; b < count; b += gridDim.x) {
+		const uint32_t i = big_list[b], g = order[i], tt = tiles_touched[g], start = offsets[i] - tt;
+		const float2 xy = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS);
+		const float2 ext = *reinterpret_cast<const float2 *>(rec + (size_t)g * GSR_REC_FLOATS + 8);
+		const int radius = (int)rec[(size_t)g * GSR_REC_FLOATS + 13];
+		int x0, y0, x1, y1;
+		get_rect(xy.x, xy.y, radius, gx, gy, x0, y0, x1, y1);
+		for (uint32_t e = threadIdx.x; e < tt; e += blockDim.x)
+			emit_one(g, (int)e, x0, y0, x1 - x0, xy.x, xy.y, ext.x, ext.y, gx, packed, keys + start + e, vals + start + e);
 	}
 }
 
@@ -237,11 +276,17 @@ cudaError_t bin_instances(int P, int64_t capacity, int W, int H, char *geom, con
 
 	const uint32_t *order = (const uint32_t *)(geom + GL.depth_val[depth_order_index()]);
 	const uint32_t *n_dev = (const uint32_t *)(geom + GL.offsets) + (P - 1);
+	uint32_t *header = (uint32_t *)(binning + BL.header);
+	uint32_t *big_list = (uint32_t *)(geom + GL.depth_key[1 - depth_order_index()]); // the depth sort's spare key array: free by now
+	if ((e = cudaMemsetAsync(header, 0, 256, stream)) != cudaSuccess) return e;
 	emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order, (const uint32_t *)(geom + GL.offsets),
 	                                                         (const uint32_t *)(geom + GL.tiles_touched), (const float *)(geom + GL.rec),
-	                                                         gx, gy, point_list_packed(P), capacity, (uint32_t *)(binning + BL.header),
+	                                                         gx, gy, point_list_packed(P), capacity, header, big_list,
 	                                                         (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
-	count_launch();
+	emit_big_kernel<<<4 * 148, 256, 0, stream>>>(P, order, (const uint32_t *)(geom + GL.offsets), (const uint32_t *)(geom + GL.tiles_touched),
+	                                            (const float *)(geom + GL.rec), gx, gy, point_list_packed(P), capacity, header, big_list,
+	                                            (uint32_t *)(binning + BL.key[0]), (uint32_t *)(binning + BL.val[0]));
+	count_launch(3);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
 

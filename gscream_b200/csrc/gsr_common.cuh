@@ -59,6 +59,7 @@ struct BinningLayout {  // "binningBuffer"; R below is the CAPACITY the buffer w
 constexpr int kHdrPacked = 0;    // 1: point_list entries carry the per-warp overlap mask above a 24-bit id, 0: plain ids
 constexpr int kHdrCount = 1;     // num_rendered as the device computed it
 constexpr int kHdrOverflow = 2;  // 1: num_rendered exceeded the buffer's capacity, the lists are empty
+constexpr int kHdrBigCount = 3;  // Gaussians whose rectangle was queued for the CTA-wide emission (gsr_binning.cu)
 
 GeomLayout geom_layout(int P);
 ImageLayout image_layout(int W, int H);
