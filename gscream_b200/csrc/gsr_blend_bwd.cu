@@ -42,72 +42,6 @@ namespace gsr {
 constexpr int kWarpsPerCta = GSR_BWD_WARPS_PER_CTA;
 constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 
-// Transpose-reduce over the lane-index bits S, S/2, ..: every lane contributes N values; afterwards v[0] on lane l is
-// the total (over the lanes that differ from l in those bits and all lower ones) of value index vidx<N, S>(l).
-// N/2 + N/4 + ... + 1 exchanges, then plain xor-adds for the remaining strides.
-template <int N, int S>
-__device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane)
-{
-	int s = S;
-#pragma unroll
-	for (int n = N / 2; n >= 1; n >>= 1, s >>= 1) {
-		const bool upper = (lane & s) != 0;
-#pragma unroll
-		for (int i = 0; i < n; i++) {
-			const float send = upper ? v[i] : v[i + n];
-			const float keep = upper ? v[i + n] : v[i];
-			v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-		}
-	}
-#pragma unroll
-	for (; s >= 1; s >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], s);
-}
-template <int N, int S>
-__device__ __forceinline__ int vidx(int lane)
-{
-	int idx = 0, s = S;
-#pragma unroll
-	for (int n = N / 2; n >= 1; n >>= 1, s >>= 1)
-		if (lane & s) idx += n;
-	return idx;
-}
-
-// The eight geometric / scalar terms of one (pixel, Gaussian) pair (CR/backward.cu:557-601) from s = G dL_dalpha and
-// w = alpha T:  dL_dG G = opacity * s, so
-//   dmean2D.x = -(o s) (dx a + dy b) W/2, dmean2D.y = -(o s) (dy c + dx b) H/2, dconic = -1/2 (o s) {dx dx, dx dy, dy dy},
-//   dopacity = s, ddepth = w g_depth, duncertainty = w g_unc.
-__device__ __forceinline__ void pair_terms(const float *ent, float s, float w, float pixf_x, float pixf_y, float gd, float gu,
-                                           float half_w, float half_h, float *v)
-{
-	const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
-	const float2 r1 = *reinterpret_cast<const float2 *>(ent + 4); // c o
-	const float dx = r0.x - pixf_x, dy = r0.y - pixf_y;
-	const float u = r1.y * s;
-	const float udx = u * dx, udy = u * dy;
-	v[0] = -(udx * r0.z + udy * r0.w) * half_w;
-	v[1] = -(udy * r1.x + udx * r0.w) * half_h;
-	v[2] = -0.5f * udx * dx;
-	v[3] = -0.5f * udx * dy;
-	v[4] = -0.5f * udy * dy;
-	v[5] = s;
-	v[6] = w * gd;
-	v[7] = w * gu;
-}
-
-// C = 32 keeps a 34-float gradient row and a 32-float gradient column per lane: 2 CTAs of 8 warps' worth of registers per
-// SM (16 warps); C <= 8 fits 3.
-#ifndef GSR_BWD_MINBLOCKS
-#define GSR_BWD_MINBLOCKS(C) ((C) <= 8 ? 3 : 2)
-#endif
-#define GSR_BWD_MINCTAS(C) (GSR_BWD_MINBLOCKS(C) * kCtasPerTile)
-
-// entries of a chunk whose state-independent parts are computed side by side in phase 1
-#ifndef GSR_BWD_SUB
-#define GSR_BWD_SUB 2
-#endif
-constexpr int kSub = GSR_BWD_SUB;
-static_assert(kChunk % kSub == 0, "sub-batches tile the chunk");
-
 // 1 / d for d in [0.01, 1]: MUFU.RCP + one Newton step, no range check (__frcp_rn's slow path is a call behind a branch)
 __device__ __forceinline__ float rcp_1ulp(float d)
 {
@@ -115,172 +49,6 @@ __device__ __forceinline__ float rcp_1ulp(float d)
 	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
 	const float e = __fmaf_rn(-d, r, 1.f);
 	return __fmaf_rn(r, e, r);
-}
-
-template <int C>
-struct BwdSmem {
-	using TR = BlendTraits<C>;
-	static constexpr int kHandoffBytes = 2 * kChunk * 32 * 4; // s[kChunk][32], w[kChunk][32]
-	static constexpr int kWarpBytes = TR::kWarpBytes + kHandoffBytes;
-};
-
-template <int C>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD_MINCTAS(C)) blend_backward_kernel(
-    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x,
-    const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
-    const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
-    const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dpixel_uncs,
-    float *__restrict__ gacc, float *__restrict__ dL_dcolors)
-{
-	using TR = BlendTraits<C>;
-	static_assert(C <= 8, "the butterfly carries at most 8 colour channels; C = 32 has its own kernel below");
-
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-
-	const int tid = threadIdx.x, lwarp = tid >> 5, lane = tid & 31;
-	const int tile = blockIdx.x / kCtasPerTile;
-	const int warp = (blockIdx.x % kCtasPerTile) * kWarpsPerCta + lwarp; // this warp's 8x4 pixel block within the tile
-	const int tile_x0 = (tile % tiles_x) * GSR_BLOCK_X, tile_y0 = (tile / tiles_x) * GSR_BLOCK_Y;
-	int bx, by;
-	warp_block_origin(warp, bx, by);
-	const int px = tile_x0 + bx + (lane & 7), py = tile_y0 + by + (lane >> 3);
-	const bool inside = px < W && py < H;
-	const float pixf_x = (float)px, pixf_y = (float)py;
-	const size_t plane = (size_t)H * W;
-	const size_t pix_id = (size_t)W * py + px;
-
-	const uint2 range = ranges[tile];
-	const int packed = (int)__ldg(header + kHdrPacked); // format of the list entries, recorded by the instance emission
-	const float T_final = inside ? final_Ts[pix_id] : 0.f;
-	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
-
-	// deepest last contributor of the warp: nothing behind it can receive gradient from these 32 pixels
-	int warp_last = last_contributor;
-#pragma unroll
-	for (int s = 16; s >= 1; s >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, s));
-	warp_last = min(warp_last, (int)(range.y - range.x));
-	if (warp_last == 0) return; // warps are independent: no barrier follows
-
-	// this pixel's upstream gradient row (colour channels, depth, uncertainty)
-	float g[C];
-	float gd = 0.f, gu = 0.f, bg_dot = 0.f;
-#pragma unroll
-	for (int ch = 0; ch < C; ch++) {
-		g[ch] = inside ? dL_dpixels[ch * plane + pix_id] : 0.f;
-		bg_dot += bg[ch] * g[ch];
-	}
-	if (inside) {
-		gd = dL_dpixel_depths[pix_id];
-		gu = dL_dpixel_uncs[pix_id];
-	}
-	float T = T_final;
-	float X = 0.f, last_alpha = 0.f, last_dot = 0.f;
-	const float half_w = 0.5f * (float)W, half_h = 0.5f * (float)H;
-	const float neg_Tfinal_bg = -T_final * bg_dot; // background term: (-T_final / (1 - alpha)) * sum_ch bg[ch] g[ch]
-
-	unsigned char *warp_smem = smem_raw + (size_t)lwarp * BwdSmem<C>::kWarpBytes;
-	float *s_s = reinterpret_cast<float *>(warp_smem + TR::kWarpBytes); // [kChunk][32]
-	float *s_w = s_s + kChunk * 32;                                     // [kChunk][32]
-
-	// back to front (CR/backward.cu:500): the feed scans list positions warp_last-1 .. 0
-	using Feed = WarpFeed<C, true>;
-	Feed feed;
-	feed.init(warp_smem, point_list + range.x, warp_last, rec, features, warp, lane, packed != 0);
-	feed.fill();
-	int m_cur = feed.issue(0);
-	int chunk = 0;
-	for (; m_cur > 0; chunk++) {
-		feed.fill();
-		const int m_next = feed.issue((chunk + 1) & 1);
-		feed.wait();
-		__syncwarp(); // every lane's copies of this chunk have landed
-		const float *ent0 = feed.stage + (chunk & 1) * TR::kStageFloats;
-
-		// ---- phase 1: the per-pixel recurrence over the chunk's entries, in depth order ----
-		// kSub entries at a time: (a) everything that does not depend on the pixel's running state — alpha, 1 / (1 - alpha), G
-		// and the dot product, kSub independent chains for the scheduler to interleave — then (b) the short carried chain
-		// (T, X).  An entry that does not touch the pixel is encoded as alpha = 0, rinv = 1, G = 0: the recurrence below then
-		// leaves T unchanged, hands X on unchanged (0 * dot + 1 * X') and produces s = w = 0, without a branch.
-		uint32_t live = 0; // bit e: some pixel of the warp received gradient from entry e
-		for (int e0 = 0; e0 < m_cur; e0 += kSub) {
-			float al[kSub], ri[kSub], Gs[kSub], dt[kSub];
-#pragma unroll
-			for (int b = 0; b < kSub; b++) {
-				const int e = e0 + b;
-				const float *ent = ent0 + e * TR::kEntryFloats; // (rows past m_cur hold stale but readable shared memory)
-				const int pos = (int)feed.q_pos[(feed.done + e) & (kRing - 1)]; // 0-based list position
-				const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
-				const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
-				const float dx = r0.x - pixf_x, dy = r0.y - pixf_y;
-				const float power = gaussian_power(r0.z, r0.w, r1.x, dx, dy);
-				const float G = expf(power);
-				const float alpha = min(0.99f, __fmul_rn(r1.y, G));
-				const bool valid = (e < m_cur) && (pos < last_contributor) && !(power > 0.0f) && !(alpha < kAlphaMin);
-				// dot = f_j . g_p over colour channels, depth and uncertainty
-				float d0 = r1.z * gd + r1.w * gu;
-				if (TR::kFeatInRec) {
-					const float4 r2 = *reinterpret_cast<const float4 *>(ent + 8);
-					const float cb = ent[12];
-					if (C > 0) d0 += r2.z * g[0];
-					if (C > 1) d0 += r2.w * g[1 % C];
-					if (C > 2) d0 += cb * g[2 % C];
-				} else {
-					float d1 = 0.f, d2 = 0.f, d3 = 0.f;
-					const float4 *f4 = reinterpret_cast<const float4 *>(ent + TR::kRecParts * 4);
-#pragma unroll
-					for (int q = 0; q < C / 4; q++) {
-						const float4 f = f4[q];
-						d0 += f.x * g[(4 * q + 0) % C];
-						d1 += f.y * g[(4 * q + 1) % C];
-						d2 += f.z * g[(4 * q + 2) % C];
-						d3 += f.w * g[(4 * q + 3) % C];
-					}
-					d0 = (d0 + d1) + (d2 + d3);
-				}
-				al[b] = valid ? alpha : 0.f;
-				ri[b] = valid ? rcp_1ulp(__fsub_rn(1.f, alpha)) : 1.f; // T / (1 - alpha) (CR/backward.cu:533) as T * rcp; also serves the background term
-				Gs[b] = valid ? G : 0.f;
-				dt[b] = valid ? d0 : 0.f;
-				if (__any_sync(0xffffffffu, valid)) live |= 1u << e;
-			}
-#pragma unroll
-			for (int b = 0; b < kSub; b++) {
-				T *= ri[b];
-				const float Xn = last_alpha * last_dot + (1.f - last_alpha) * X;
-				const float dL_dalpha = (dt[b] - Xn) * T + neg_Tfinal_bg * ri[b];
-				s_s[(e0 + b) * 32 + lane] = Gs[b] * dL_dalpha;
-				s_w[(e0 + b) * 32 + lane] = al[b] * T;
-				X = Xn;
-				last_alpha = al[b];
-				last_dot = dt[b];
-			}
-		}
-		__syncwarp(); // s and w of the chunk are visible to every lane
-
-		// ---- phase 2: per-Gaussian sums over the warp's 32 pixels; entries are independent of each other ----
-		{
-			while (live) {
-				const int e = __ffs(live) - 1;
-				live &= live - 1;
-				float v[16];
-				const float w = s_w[e * 32 + lane];
-				pair_terms(ent0 + e * TR::kEntryFloats, s_s[e * 32 + lane], w, pixf_x, pixf_y, gd, gu, half_w, half_h, v);
-#pragma unroll
-				for (int ch = 0; ch < 8; ch++) v[8 + ch] = ch < C ? w * g[ch % C] : 0.f;
-				warp_transpose_reduce<16, 16>(v, lane);
-				if ((lane & 1) == 0) {
-					const uint32_t id = feed.q_id[(feed.done + e) & (kRing - 1)];
-					const int q = vidx<16, 16>(lane);
-					if (q < 8) red_add(gacc + (size_t)id * 8 + q, v[0]);
-					else if (q < 8 + C) red_add(dL_dcolors + (size_t)id * C + (q - 8), v[0]);
-				}
-			}
-		}
-		feed.done += m_cur;
-		__syncwarp(); // the stage buffer, the ring slots and the s / w rows of this chunk may be reused
-		m_cur = m_next;
-	}
-	feed.drain();
 }
 
 // ---- C = 32 -----------------------------------------------------------------------------------------------------------------
@@ -305,23 +73,31 @@ __device__ __forceinline__ int kperm(int ks, int t, int half) { return 16 * (ks 
 
 constexpr int kDotStride = 20;     // floats per pixel row of the dot tile (16 entries + pad: conflict-free LDS.128 by lane = pixel)
 constexpr int kSub32 = 4;          // entries per recurrence sub-batch (one LDS.128 of dots)
-struct Bwd32Smem {
-	using TR = BlendTraits<32>;
+template <int C>
+struct BwdSmem {
+	using TR = BlendTraits<C>;
 	static constexpr int kS = TR::kWarpBytes, kW = kS + kChunk * 32 * 4, kDot = kW + kChunk * 32 * 4;
-	static constexpr int kWarpBytes = kDot + 32 * kDotStride * 4;
+	static constexpr int kWarpBytes = kDot + (C == 32 ? 32 * kDotStride * 4 : 0);
 };
+// resident CTAs (of kWarpsPerCta warps) per SM asked of ptxas.  C = 32: 164 registers (the gradient block twice, 72 registers of
+// operands) -> 12 warps per SM; 144 / 128 registers spill and are 13 % / 60 % slower (profiles/r2_blend_mma.md)
 #ifndef GSR_BWD32_MINCTAS
 #define GSR_BWD32_MINCTAS 6
 #endif
+#ifndef GSR_BWD3_MINCTAS
+#define GSR_BWD3_MINCTAS 10
+#endif
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_backward_c32_kernel(
+template <int C>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, C == 32 ? GSR_BWD32_MINCTAS : GSR_BWD3_MINCTAS) blend_backward_kernel(
     const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x,
     const float *__restrict__ rec, const float *__restrict__ features, const float *__restrict__ bg,
     const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dpixel_uncs,
     float *__restrict__ gacc, float *__restrict__ dL_dcolors)
 {
-	constexpr int C = 32;
+	constexpr bool kWide = (C == 32); // feature rows beside the record, dot products and colour sums on the tensor pipe
+	static_assert(kWide || C == 3, "instantiated for the two channel counts of the C ABI");
 	using TR = BlendTraits<C>;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 
@@ -356,18 +132,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 		return (x < W && y < H) ? (long long)W * y + x : -1;
 	};
 	// the block's 32 x 32 upstream colour gradient, as the A operand of the dot product (rows = pixels, k = channels) ...
-	float gA[2][4][4];
+	float gA[kWide ? 2 : 1][4][4];
+	if (kWide) {
 #pragma unroll
-	for (int mt = 0; mt < 2; mt++)
+		for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const long long off = pix_off(16 * mt + gq + 8 * (j & 1));
+			for (int j = 0; j < 4; j++) {
+				const long long off = pix_off(16 * mt + gq + 8 * (j & 1));
 #pragma unroll
-			for (int ks = 0; ks < 4; ks++) gA[mt][ks][j] = off >= 0 ? __ldg(dL_dpixels + (size_t)kperm(ks, t, j >> 1) * plane + off) : 0.f;
-		}
+				for (int ks = 0; ks < 4; ks++) gA[mt % (kWide ? 2 : 1)][ks][j] = off >= 0 ? __ldg(dL_dpixels + (size_t)kperm(ks, t, j >> 1) * plane + off) : 0.f;
+			}
+	}
 	// ... and as the B operand of the colour sums (k = pixels, columns = channels): channel 8 nt + gq, pixels 16 kk + 4 t .. + 3
-	float gB[4][4][2];
-	{
+	float gB[4][kWide ? 4 : 1][2];
+	if (kWide) {
 		const bool vec_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0) && (x0 + 8 <= W);
 #pragma unroll
 		for (int nt = 0; nt < 4; nt++)
@@ -383,19 +161,23 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 #pragma unroll
 					for (int j = 0; j < 4; j++) v[j] = (xx + j < W && y < H) ? __ldg(src + (size_t)W * y + xx + j) : 0.f;
 				}
-				gB[2 * kk][nt][0] = v[0]; gB[2 * kk][nt][1] = v[1];
-				gB[2 * kk + 1][nt][0] = v[2]; gB[2 * kk + 1][nt][1] = v[3];
+				gB[2 * kk][nt % (kWide ? 4 : 1)][0] = v[0]; gB[2 * kk][nt % (kWide ? 4 : 1)][1] = v[1];
+				gB[2 * kk + 1][nt % (kWide ? 4 : 1)][0] = v[2]; gB[2 * kk + 1][nt % (kWide ? 4 : 1)][1] = v[3];
 			}
 	}
-	// columns 32, 33 of that operand: the depth and uncertainty gradients (lanes gq = 0, 1; the other columns of the tile are zero)
+	// one more 8-column tile of that operand: the depth and uncertainty gradients (columns gq = 0, 1) and, for C = 3, the three
+	// colour gradients (columns 2..4); the other columns are zero
 	float gY[4][2];
+	{
+		const float *col = gq == 0 ? dL_dpixel_depths : gq == 1 ? dL_dpixel_uncs : (!kWide && gq < 2 + C) ? dL_dpixels + (size_t)(gq - 2) * plane : nullptr;
 #pragma unroll
-	for (int ks = 0; ks < 4; ks++)
+		for (int ks = 0; ks < 4; ks++)
 #pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const long long off = pix_off(kperm(ks, t, h));
-			gY[ks][h] = (gq < 2 && off >= 0) ? __ldg((gq == 0 ? dL_dpixel_depths : dL_dpixel_uncs) + off) : 0.f;
-		}
+			for (int h = 0; h < 2; h++) {
+				const long long off = pix_off(kperm(ks, t, h));
+				gY[ks][h] = (col != nullptr && off >= 0) ? __ldg(col + off) : 0.f;
+			}
+	}
 
 	// operand of the moment product: column gq is the monomial {1, cx, cy, cx^2, cx cy, cy^2, 0, 0}[gq] of the slot's pixel in
 	// block-centred coordinates
@@ -413,8 +195,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 
 	// lane = pixel quantities
 	const float gd = inside ? dL_dpixel_depths[pix_id] : 0.f, gu = inside ? dL_dpixel_uncs[pix_id] : 0.f;
+	float grow[kWide ? 1 : C]; // C = 3: this pixel's colour gradient row (the dot product is three FFMA)
 	float bg_dot = 0.f;
-	{
+	if (!kWide) {
+#pragma unroll
+		for (int ch = 0; ch < (kWide ? 0 : C); ch++) {
+			grow[ch] = inside ? dL_dpixels[ch * plane + pix_id] : 0.f;
+			bg_dot += bg[ch] * grow[ch];
+		}
+	} else {
 		const float bgv = bg[lane];
 		if (__any_sync(0xffffffffu, bgv != 0.f)) {
 #pragma unroll 4
@@ -427,10 +216,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 	const float neg_Tfinal_bg = -T_final * bg_dot; // background term: (-T_final / (1 - alpha)) * sum_ch bg[ch] g[ch]
 	const float blk_cx = (float)x0 + 3.5f, blk_cy = (float)y0 + 1.5f;
 
-	unsigned char *warp_smem = smem_raw + (size_t)lwarp * Bwd32Smem::kWarpBytes;
-	float *s_s = reinterpret_cast<float *>(warp_smem + Bwd32Smem::kS);   // [kChunk][32]
-	float *s_w = reinterpret_cast<float *>(warp_smem + Bwd32Smem::kW);   // [kChunk][32]
-	float *s_dot = reinterpret_cast<float *>(warp_smem + Bwd32Smem::kDot); // [32][kDotStride]
+	unsigned char *warp_smem = smem_raw + (size_t)lwarp * BwdSmem<C>::kWarpBytes;
+	float *s_s = reinterpret_cast<float *>(warp_smem + BwdSmem<C>::kS);   // [kChunk][32]
+	float *s_w = reinterpret_cast<float *>(warp_smem + BwdSmem<C>::kW);   // [kChunk][32]
+	float *s_dot = reinterpret_cast<float *>(warp_smem + BwdSmem<C>::kDot); // [32][kDotStride]
 
 	// back to front (CR/backward.cu:500): the feed scans list positions warp_last-1 .. 0
 	using Feed = WarpFeed<C, true>;
@@ -446,8 +235,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 		__syncwarp(); // every lane's copies of this chunk have landed
 		const float *ent0 = feed.stage + (chunk & 1) * TR::kStageFloats;
 
-		// ---- phase 0: dot[p][e] for the whole chunk on the tensor pipe (rows past m_cur: stale operands, results unused) ----
-		{
+		// ---- phase 0 (C = 32): dot[p][e] for the whole chunk on the tensor pipe (rows past m_cur: stale operands, results unused) ----
+		if (kWide) {
 			float D[2][2][4];
 #pragma unroll
 			for (int mt = 0; mt < 2; mt++)
@@ -472,7 +261,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 					for (int mt = 0; mt < 2; mt++) {
 						uint32_t ah[4], al[4];
 #pragma unroll
-						for (int j = 0; j < 4; j++) split_tf32(gA[mt][2 * kk + sub][j], ah[j], al[j]);
+						for (int j = 0; j < 4; j++) split_tf32(gA[mt % (kWide ? 2 : 1)][2 * kk + sub][j], ah[j], al[j]);
 #pragma unroll
 						for (int nt = 0; nt < 2; nt++) mma3_tf32(D[mt][nt], ah, al, bh[nt][2 * sub], bh[nt][2 * sub + 1], bl[nt][2 * sub], bl[nt][2 * sub + 1]);
 					}
@@ -485,8 +274,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 					*reinterpret_cast<float2 *>(s_dot + (16 * mt + gq) * kDotStride + 8 * nt + 2 * t) = make_float2(D[mt][nt][0], D[mt][nt][1]);
 					*reinterpret_cast<float2 *>(s_dot + (16 * mt + gq + 8) * kDotStride + 8 * nt + 2 * t) = make_float2(D[mt][nt][2], D[mt][nt][3]);
 				}
+			__syncwarp();
 		}
-		__syncwarp();
 
 		// ---- phase 1 (lane = pixel): the recurrence over the chunk's entries, in depth order ----
 		// kSub32 entries at a time: (a) everything that does not depend on the pixel's running state — alpha, 1 / (1 - alpha), G —
@@ -494,8 +283,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 		// G = 0: the recurrence then leaves T unchanged, hands X on unchanged (0 * dot + 1 * X') and produces s = w = 0.
 		uint32_t live = 0; // bit e: some pixel of the warp received gradient from entry e
 		for (int e0 = 0; e0 < m_cur; e0 += kSub32) {
-			const float4 d4 = *reinterpret_cast<const float4 *>(s_dot + lane * kDotStride + e0);
-			const float dcol[4] = {d4.x, d4.y, d4.z, d4.w};
+			float dcol[4] = {0.f, 0.f, 0.f, 0.f};
+			if (kWide) {
+				const float4 d4 = *reinterpret_cast<const float4 *>(s_dot + lane * kDotStride + e0);
+				dcol[0] = d4.x; dcol[1] = d4.y; dcol[2] = d4.z; dcol[3] = d4.w;
+			}
 			float al[kSub32], ri[kSub32], Gs[kSub32], dt[kSub32];
 #pragma unroll
 			for (int b = 0; b < kSub32; b++) {
@@ -512,7 +304,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 				al[b] = valid ? alpha : 0.f;
 				ri[b] = valid ? rcp_1ulp(__fsub_rn(1.f, alpha)) : 1.f; // T / (1 - alpha) (CR/backward.cu:533) as T * rcp; also serves the background term
 				Gs[b] = valid ? G : 0.f;
-				dt[b] = valid ? dcol[b] + (r1.z * gd + r1.w * gu) : 0.f; // f_j . g_p over colour channels, depth and uncertainty
+				float dot = r1.z * gd + r1.w * gu; // f_j . g_p over colour channels, depth and uncertainty
+				if (kWide) {
+					dot += dcol[b];
+				} else { // the colours ride in the record (slots 10..12)
+					const float4 r2 = *reinterpret_cast<const float4 *>(ent + 8);
+					dot += r2.z * grow[0] + r2.w * grow[1 % (kWide ? 1 : C)] + ent[12] * grow[2 % (kWide ? 1 : C)];
+				}
+				dt[b] = valid ? dot : 0.f;
 				if (__any_sync(0xffffffffu, valid)) live |= 1u << e;
 			}
 #pragma unroll
@@ -553,12 +352,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 					uint32_t ah[4], al[4];
 #pragma unroll
 					for (int j = 0; j < 4; j++) split_tf32(wv[sub][j], ah[j], al[j]);
+					if (kWide) {
 #pragma unroll
-					for (int nt = 0; nt < 4; nt++) {
-						uint32_t b0h, b0l, b1h, b1l;
-						split_tf32(gB[ks][nt][0], b0h, b0l);
-						split_tf32(gB[ks][nt][1], b1h, b1l);
-						mma3_tf32(Dc[nt], ah, al, b0h, b1h, b0l, b1l);
+						for (int nt = 0; nt < 4; nt++) {
+							uint32_t b0h, b0l, b1h, b1l;
+							split_tf32(gB[ks][nt % (kWide ? 4 : 1)][0], b0h, b0l);
+							split_tf32(gB[ks][nt % (kWide ? 4 : 1)][1], b1h, b1l);
+							mma3_tf32(Dc[nt], ah, al, b0h, b1h, b0l, b1l);
+						}
 					}
 					{
 						uint32_t b0h, b0l, b1h, b1l;
@@ -579,9 +380,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 				const int e = gq + 8 * r;
 				const bool on = e < m_cur && ((live >> e) & 1u);
 				const uint32_t id = feed.q_id[(feed.done + e) & (kRing - 1)];
-				if (on) {
+				if (on && kWide) {
 #pragma unroll
 					for (int nt = 0; nt < 4; nt++) red_add_v2(dL_dcolors + (size_t)id * C + 8 * nt + 2 * t, Dc[nt][2 * r], Dc[nt][2 * r + 1]);
+				}
+				if (on && !kWide) { // columns 2..4 of the last tile: lane t = 1 holds channels 0, 1 and lane t = 2 channel 2
+					if (t == 1) {
+						red_add(dL_dcolors + (size_t)id * C + 0, Dy[2 * r]);
+						red_add(dL_dcolors + (size_t)id * C + 1, Dy[2 * r + 1]);
+					} else if (t == 2) {
+						red_add(dL_dcolors + (size_t)id * C + 2, Dy[2 * r]);
+					}
 				}
 				// the quad's four lanes hold the row's moments pairwise (t = 0: M0 Mx, 1: My Mxx, 2: Mxy Myy) and (t = 0) the depth /
 				// uncertainty sums; every lane fetches all of them and forms its own pair of the eight outputs
@@ -613,22 +422,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, GSR_BWD32_MINCTAS) blend_ba
 	feed.drain();
 }
 
-static cudaError_t launch_bwd32(int tiles, const uint2 *ranges, const uint32_t *point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x, const float *rec,
-                                const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
-                                const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
-                                float *dL_dcolors, cudaStream_t stream)
-{
-	constexpr int smem = kWarpsPerCta * Bwd32Smem::kWarpBytes;
-	cudaError_t e = cudaFuncSetAttribute(blend_backward_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	if (e != cudaSuccess) return e;
-	blend_backward_c32_kernel<<<tiles * kCtasPerTile, 32 * kWarpsPerCta, smem, stream>>>(ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib,
-	                                                                                  dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors);
-	count_launch();
-	return cudaGetLastError();
-}
-
 template <int C>
-static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, const uint32_t *__restrict__ header, int W, int H, int tiles_x, const float *rec,
+static cudaError_t launch_bwd(int tiles, const uint2 *ranges, const uint32_t *point_list, const uint32_t *header, int W, int H, int tiles_x, const float *rec,
                               const float *features, const float *bg, const float *final_Ts, const uint32_t *n_contrib,
                               const float *dL_dpixels, const float *dL_dpixel_depths, const float *dL_dpixel_uncs, float *gacc,
                               float *dL_dcolors, cudaStream_t stream)
@@ -653,7 +448,7 @@ cudaError_t launch_blend_backward(int C, int W, int H, const uint2 *ranges, cons
 	if (tiles <= 0) return cudaSuccess;
 	switch (C) {
 	case 3: return launch_bwd<3>(tiles, ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
-	case 32: return launch_bwd32(tiles, ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
+	case 32: return launch_bwd<32>(tiles, ranges, point_list, header, W, H, tiles_x, rec, features, bg, final_Ts, n_contrib, dL_dpixels, dL_dpixel_depths, dL_dpixel_uncs, gacc, dL_dcolors, stream);
 	default: return cudaErrorInvalidValue;
 	}
 }
