@@ -616,7 +616,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     out = run_ours(args, cfg, rank, world, local)
-    if rank == 0 and world == 1 and args.workload == "config3" and args.scale_mult == 1.0 and not args.no_other_configs:
+    if rank == 0 and world == 1 and args.workload == "config3" and args.scale_mult == 1.0 and not args.no_other_configs and not args.value_only:
         torch.cuda.empty_cache()
         out["other_configs"] = other_configs()
     if rank == 0:
