@@ -220,9 +220,22 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             out.get("dL_dcov3D"), out.get("dL_dsh"), out["dL_dscales"], out["dL_drotations"])
 
 
+def _rows3(t, name):
+    """(tensor, row stride in floats) of a [P,3] float32 CUDA tensor.  A row-strided view with unit inner stride — GScream hands
+    the filters `get_scaling[:, :3]` of a [A,6] tensor (gaussian_renderer/__init__.py:298) — is read in place by the kernel
+    instead of through the contiguous copy the reference makes (rasterize_points.cu:280)."""
+    if t is None or t.numel() == 0:
+        return t, 3
+    if (t.dim() == 2 and t.size(1) == 3 and t.dtype == torch.float32 and t.is_cuda and t.stride(1) == 1
+            and t.stride(0) >= 3 and t.data_ptr() % 4 == 0):
+        return t, int(t.stride(0))
+    return _f32c(t, name), 3
+
+
 def _filter_common(means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix):
     _check_means(means3D)
-    return (_f32c(means3D, "means3D"), _f32c(scales, "scales"), _f32c(rotations, "rotations"),
+    scales, stride = _rows3(scales, "scales")
+    return (_f32c(means3D, "means3D"), scales, stride, _f32c(rotations, "rotations"),
             _f32c(cov3D_precomp, "cov3D_precomp"), _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix"))
 
 
@@ -237,13 +250,13 @@ def rasterize_aussians_filter(means3D, scales, rotations, scale_modifier, cov3D_
     _check_means(means3D)
     dev = means3D.device
     with torch.cuda.device(dev):
-        means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix = _filter_common(
+        means3D, scales, scales_stride, rotations, cov3D_precomp, viewmatrix, projmatrix = _filter_common(
             means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix)
         P = means3D.size(0)
-        radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)  # every element is written
         if P != 0:
             _lib.check(lib.gsr_visible_filter(
-                P, _ptr(means3D), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
+                P, _ptr(means3D), _ptr(scales), scales_stride, float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                 _ptr(projmatrix), int(image_width), int(image_height), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
                 radii.data_ptr(), _stream()))
             if debug:
@@ -263,7 +276,7 @@ def rasterize_aussians_filter_position2D(means3D, scales, rotations, scale_modif
     _check_means(means3D)
     dev = means3D.device
     with torch.cuda.device(dev):
-        means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix = _filter_common(
+        means3D, scales, scales_stride, rotations, cov3D_precomp, viewmatrix, projmatrix = _filter_common(
             means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix)
         P = means3D.size(0)
         radii = torch.zeros((P,), dtype=torch.int32, device=dev)
@@ -271,7 +284,7 @@ def rasterize_aussians_filter_position2D(means3D, scales, rotations, scale_modif
         y = torch.zeros((P,), dtype=torch.float32, device=dev)
         if P != 0:
             _lib.check(lib.gsr_position2d_filter(
-                P, _ptr(means3D), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
+                P, _ptr(means3D), _ptr(scales), scales_stride, float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                 _ptr(projmatrix), int(image_width), int(image_height), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
                 radii.data_ptr(), x.data_ptr(), y.data_ptr(), _stream()))
             if debug:

@@ -25,8 +25,8 @@ PROTOTYPES = {
     "gsr_forward_stage2": (_i, [_i, _i, _i64, _vp, _vp, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
     "gsr_backward": (_i, [_i, _i, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp,
                           _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "gsr_visible_filter": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp]),
-    "gsr_position2d_filter": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
+    "gsr_visible_filter": (_i, [_i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp]),
+    "gsr_position2d_filter": (_i, [_i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "gsr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gsr_debug_export": (_i, [_i, _i64, _i, _i, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsr_decode_supported": (_i, [_i, _i]),

@@ -130,6 +130,7 @@ int gsr_forward_stage1(int P, int C, int sh_degree, int M, const float *means3D,
 	a.cov3D_precomp = cov3D_precomp; a.shs = shs; a.colors_precomp = colors_precomp;
 	a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
 	a.scale_modifier = scale_modifier;
+	a.scales_stride = 3;
 	a.W = width; a.H = height;
 	a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
 	a.focal_y = height / (2.0f * tan_fovy); // CR/rasterizer_impl.cu:226-227
@@ -270,7 +271,7 @@ int gsr_profile_read(int stage, float *ms_host, int capacity)
 	return n;
 }
 
-static int run_filter(int mode, int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+static int run_filter(int mode, int P, const float *means3D, const float *scales, int scales_stride, float scale_modifier, const float *rotations,
                       const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, int width, int height,
                       float tan_fovx, float tan_fovy, int prefiltered, int *radii, float *px, float *py, cudaStream_t stream)
 {
@@ -280,8 +281,10 @@ static int run_filter(int mode, int P, const float *means3D, const float *scales
 	if (!cov3D_precomp && (!scales || !rotations)) return GSR_E_BADARG;
 	if (rotations && !aligned16(rotations)) return GSR_E_BADARG;
 	if (mode == 2 && (!px || !py)) return GSR_E_BADARG;
+	if (scales && scales_stride < 3) return GSR_E_BADARG;
 	PreArgs a{};
 	a.P = P; a.C = 3;
+	a.scales_stride = scales_stride;
 	a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
 	a.view = viewmatrix; a.proj = projmatrix;
 	a.scale_modifier = scale_modifier;
@@ -297,20 +300,20 @@ static int run_filter(int mode, int P, const float *means3D, const float *scales
 	return 0;
 }
 
-int gsr_visible_filter(int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+int gsr_visible_filter(int P, const float *means3D, const float *scales, int scales_stride, float scale_modifier, const float *rotations,
                        const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, int width, int height,
                        float tan_fovx, float tan_fovy, int prefiltered, int *radii, gsr_stream_t stream)
 {
-	return run_filter(1, P, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, width, height, tan_fovx,
+	return run_filter(1, P, means3D, scales, scales_stride, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, width, height, tan_fovx,
 	                  tan_fovy, prefiltered, radii, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int gsr_position2d_filter(int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+int gsr_position2d_filter(int P, const float *means3D, const float *scales, int scales_stride, float scale_modifier, const float *rotations,
                           const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, int width, int height,
                           float tan_fovx, float tan_fovy, int prefiltered, int *radii, float *position2D_x, float *position2D_y,
                           gsr_stream_t stream)
 {
-	return run_filter(2, P, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, width, height, tan_fovx,
+	return run_filter(2, P, means3D, scales, scales_stride, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, width, height, tan_fovx,
 	                  tan_fovy, prefiltered, radii, position2D_x, position2D_y, (cudaStream_t)stream);
 }
 

@@ -10,6 +10,7 @@ struct PreArgs {
 	const float *means3D, *scales, *rotations, *opacities, *uncertainties, *cov3D_precomp, *shs, *colors_precomp;
 	const float *view, *proj, *campos;
 	float scale_modifier;
+	int scales_stride;   // floats between consecutive rows of `scales` (3 = contiguous)
 	int W, H;
 	float tan_fovx, tan_fovy, focal_x, focal_y;
 	int gx, gy;

@@ -222,8 +222,16 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 	const int first = blockIdx.x * 256;
 	const int rows = min(256, a.P - first);
 	stage_rows<3>(a.means3D, first, rows, s_xyz);
-	if (a.cov3D_precomp == nullptr)
-		stage_rows<3>(a.scales, first, rows, s_scale);
+	if (a.cov3D_precomp == nullptr) {
+		if (a.scales_stride == 3) {
+			stage_rows<3>(a.scales, first, rows, s_scale);
+		} else if ((int)threadIdx.x < rows) {
+			// a row-strided view: the anchor filters are called with `get_scaling[:, :3]` of a [A, 6] tensor
+			// (gaussian_renderer/__init__.py:298); read in place instead of through a contiguous copy
+			const float *row = a.scales + (size_t)(first + threadIdx.x) * a.scales_stride;
+			s_scale[3 * threadIdx.x] = __ldg(row); s_scale[3 * threadIdx.x + 1] = __ldg(row + 1); s_scale[3 * threadIdx.x + 2] = __ldg(row + 2);
+		}
+	}
 	if (threadIdx.x < 16) s_view[threadIdx.x] = a.view[threadIdx.x];
 	else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = a.proj[threadIdx.x - 16];
 	__syncthreads();

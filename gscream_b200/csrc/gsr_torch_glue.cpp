@@ -194,7 +194,7 @@ Tensor rasterize_aussians_filter(const Tensor &means3D, const Tensor &scales, co
 		const c10::cuda::CUDAGuard guard(means3D.device());
 		const F32 m3(means3D, "means3D"), sc(scales, "scales"), ro(rotations, "rotations"), cov(cov3D_precomp, "cov3D_precomp"),
 		    view(viewmatrix, "viewmatrix"), proj(projmatrix, "projmatrix");
-		check_rc(gsr_visible_filter(P, m3.ptr(), sc.ptr(), scale_modifier, ro.ptr(), cov.ptr(), view.ptr(), proj.ptr(), image_width, image_height,
+		check_rc(gsr_visible_filter(P, m3.ptr(), sc.ptr(), 3, scale_modifier, ro.ptr(), cov.ptr(), view.ptr(), proj.ptr(), image_width, image_height,
 		                            tan_fovx, tan_fovy, prefiltered ? 1 : 0, radii.data_ptr<int>(), current_stream()));
 		if (debug) AT_CUDA_CHECK(cudaDeviceSynchronize());
 	}
@@ -216,7 +216,7 @@ std::tuple<Tensor, Tensor, Tensor> rasterize_aussians_filter_position2D(const Te
 		const c10::cuda::CUDAGuard guard(means3D.device());
 		const F32 m3(means3D, "means3D"), sc(scales, "scales"), ro(rotations, "rotations"), cov(cov3D_precomp, "cov3D_precomp"),
 		    view(viewmatrix, "viewmatrix"), proj(projmatrix, "projmatrix");
-		check_rc(gsr_position2d_filter(P, m3.ptr(), sc.ptr(), scale_modifier, ro.ptr(), cov.ptr(), view.ptr(), proj.ptr(), image_width,
+		check_rc(gsr_position2d_filter(P, m3.ptr(), sc.ptr(), 3, scale_modifier, ro.ptr(), cov.ptr(), view.ptr(), proj.ptr(), image_width,
 		                               image_height, tan_fovx, tan_fovy, prefiltered ? 1 : 0, radii.data_ptr<int>(), x.data_ptr<float>(),
 		                               y.data_ptr<float>(), current_stream()));
 		if (debug) AT_CUDA_CHECK(cudaDeviceSynchronize());

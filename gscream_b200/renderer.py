@@ -13,7 +13,8 @@ Same names, signatures and return values as the reference module, so train.py:43
   prefilter_position2D_debug(...) -> (radii, x, y)        gaussian_renderer/__init__.py:306-359
       the anchor filters allocate no scratch (the reference allocates full geometry + image buffers there,
       CR/rasterizer_impl.cu:493-508) and never build the unused `screenspace_points` tensor of the reference's prefilters
-      (:197-201, an autograd leaf nothing reads); the `pc.get_scaling[:, :3]` slice is still made contiguous (1.2 MB at 10^5 anchors).
+      (:197-201, an autograd leaf nothing reads); the `pc.get_scaling[:, :3]` slice is read in place through its row stride
+      (the reference copies it, rasterize_points.cu:280).
 
 `viewpoint_camera` needs the attributes the reference reads: FoVx, FoVy, image_height, image_width, world_view_transform,
 full_proj_transform, camera_center (scene/cameras.py:64-69); `pipe`: debug, compute_cov3D_python; `pc`: the GaussianModel

@@ -140,15 +140,17 @@ GSR_API int gsr_backward(
     int accumulate, gsr_stream_t stream);
 
 /* Anchor pre-filters — replace Rasterizer::visible_filter / position2D_filter /
- * markVisible (CR/rasterizer_impl.cu:350-406, 470-530, 141-153).  No scratch needed. */
+ * markVisible (CR/rasterizer_impl.cu:350-406, 470-530, 141-153).  No scratch needed.
+ * scales_stride: floats between consecutive rows of `scales` (3 = contiguous [P,3]).  GScream calls the filters with
+ * `get_scaling[:, :3]`, a row-strided view of a [A,6] tensor (gaussian_renderer/__init__.py:298): it is read in place. */
 GSR_API int gsr_visible_filter(
-    int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+    int P, const float *means3D, const float *scales, int scales_stride, float scale_modifier, const float *rotations,
     const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
     int width, int height, float tan_fovx, float tan_fovy, int prefiltered,
     int *radii, gsr_stream_t stream);
 
 GSR_API int gsr_position2d_filter(
-    int P, const float *means3D, const float *scales, float scale_modifier, const float *rotations,
+    int P, const float *means3D, const float *scales, int scales_stride, float scale_modifier, const float *rotations,
     const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
     int width, int height, float tan_fovx, float tan_fovy, int prefiltered,
     int *radii, float *position2D_x, float *position2D_y, gsr_stream_t stream);

@@ -65,7 +65,7 @@ def test_argument_validation_without_device(lib):
                                 0, 64, 0.5, 0.5, 0, None, None, 0, ctypes.addressof(n), None)
     assert rc == -1  # bad image size
     assert lib.gsr_mark_visible(0, None, None, None, None, None) == 0
-    assert lib.gsr_visible_filter(5, None, None, 1.0, None, None, None, None, 64, 64, 0.5, 0.5, 0, None, None) == -1
+    assert lib.gsr_visible_filter(5, None, None, 3, 1.0, None, None, None, None, 64, 64, 0.5, 0.5, 0, None, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
