@@ -380,7 +380,7 @@ def run_ours(args, cfg, rank, world, local):
                        "views_per_step": world, "num_rendered": R, "visible": V, "instances_per_gaussian": R / max(P, 1),
                        "tile_list_len": tile_stats, "parallelism": "view-parallel dp%d" % world,
                        "l2": "working set (features 128 MB + records 64 MB + planes 282 MB x2) exceeds the 126 MB L2; no explicit flush",
-                       "collective": "1 NCCL sum-allreduce of the %.0f MB gradient bucket per step" % (bucket.nbytes() / 1e6) if world > 1 else "none (1 GPU)"},
+                       "collective": ("1 NCCL sum-allreduce of the %.0f MB parameter-gradient bucket per step (the per-view means2D block stays local)" % (bucket.reduced_nbytes() / 1e6)) if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d_view_bytes, "d2h_bytes_per_step": 4,
                     "note": "public GaussianRasterizer API + autograd; per step the camera and the view's upstream-gradient planes (C colour + depth + uncertainty) are copied from pinned host memory (double-buffered on a copy stream), the Gaussian arrays are resident like model weights. Device -> host: ONE scalar (4 bytes) — the rendered planes are NOT copied back, their consumer (the loss) lives on the device as in GScream (scene/cameras.py keeps the images on the GPU). At config3 the 282 MB of upload per step make this number a measurement of the PCIe link, not of the kernels"},
             "e2e_device_resident_api": {"value": api_value, "unit": "views/s", "ms_per_step": api_ms / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -6,14 +6,22 @@ v % world_size, every rank accumulates the per-Gaussian gradients of its views i
 (the backward kernels add straight into it, `accumulate=1` in the C ABI — no per-view temporaries), and a
 single sum-allreduce of that bucket per step (NCCL over NVLink/NVSwitch; gloo in the CPU tests) makes the
 gradients identical on every rank.  There is no other data-path collective.
+
+Bucket order: the colour block first (two thirds of the bucket at C = 32; final as soon as the blend backward is done), then
+the other parameter gradients, then — outside the all-reduced range — the screen-space means2D gradients: they are the
+per-view signal of the densification statistics (scene/gaussian_model.py:755), not a parameter gradient, and SURVEY 8e's
+bucket does not carry them (44 floats per Gaussian at C = 32).  (Starting the collective on the colour block on a side stream
+while the per-Gaussian backward kernel still runs was built and measured: two collectives cost more than the 0.08 ms they hide,
+profiles/r2_scaling.md.)
 """
 from typing import Dict, List, Sequence
 
 import torch
 
 # (name, columns) of the per-Gaussian gradient blocks in bucket order; C is filled in at construction.
-_BLOCKS = (("means3D", 3), ("means2D", 3), ("colors", None), ("opacities", 1), ("uncertainties", 1),
-           ("scales", 3), ("rotations", 4))
+_BLOCKS = (("colors", None), ("means3D", 3), ("opacities", 1), ("uncertainties", 1), ("scales", 3), ("rotations", 4),
+           ("means2D", 3))
+_LOCAL_ONLY = ("means2D",)   # kept per rank, not all-reduced
 
 
 def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
@@ -35,6 +43,8 @@ class GradBucket:
             self.layout.append((name, off, cols))
             off += self.P * cols
         self.numel = off
+        self.reduced_numel = sum(self.P * cols for name, _, cols in self.layout if name not in _LOCAL_ONLY)  # a prefix of the buffer
+        self.colors_numel = self.P * self.C                                                                  # ... and its first block
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.views: Dict[str, torch.Tensor] = {
             name: self.flat[o:o + self.P * cols].view(self.P, cols) for name, o, cols in self.layout}
@@ -45,6 +55,10 @@ class GradBucket:
 
     def nbytes(self) -> int:
         return self.numel * 4
+
+    def reduced_nbytes(self) -> int:
+        """Bytes the per-step collective moves (the parameter gradients; the per-view means2D block stays local)."""
+        return self.reduced_numel * 4
 
     def as_backward_out(self) -> Dict[str, torch.Tensor]:
         """Mapping expected by gscream_b200._C.rasterize_gaussians_backward(out=..., accumulate=True)."""
@@ -59,9 +73,10 @@ def allreduce_bucket(bucket: GradBucket, group=None, average: bool = False):
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return bucket
-    dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=group)
+    red = bucket.flat[:bucket.reduced_numel]
+    dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
     if average:
-        bucket.flat.div_(dist.get_world_size(group))
+        red.div_(dist.get_world_size(group))
     return bucket
 
 

@@ -24,6 +24,9 @@ def test_bucket_layout_is_one_flat_buffer_of_contiguous_blocks():
     P, C = 11, 32
     b = GradBucket(P, C)
     assert b.numel == P * (3 + 3 + C + 1 + 1 + 3 + 4) and b.nbytes() == b.numel * 4
+    # the all-reduced range is a prefix that starts with the colour block and leaves out the per-view means2D block
+    assert b.reduced_numel == P * (3 + C + 1 + 1 + 3 + 4) and b.colors_numel == P * C
+    assert b.layout[0][0] == "colors" and b.layout[-1][0] == "means2D" and b.layout[-1][1] == b.reduced_numel
     total = 0
     for name, off, cols in b.layout:
         v = b.views[name]
@@ -54,8 +57,11 @@ def _worker(rank, world, port, n_views, q):
     # stand-in for "backward of view v adds its gradient": view v contributes (v+1) to every entry
     for v in shard_views(n_views, world, rank):
         bucket.flat.add_(float(v + 1))
+    local_sum = float(sum(v + 1 for v in shard_views(n_views, world, rank)))
     allreduce_bucket(bucket)
-    q.put((rank, bucket.flat.clone()))
+    # the per-view means2D block is not part of the collective: it keeps this rank's own sum
+    assert torch.all(bucket.views["means2D"] == local_sum)
+    q.put((rank, bucket.flat[:bucket.reduced_numel].clone()))
     dist.barrier()
     dist.destroy_process_group()
 

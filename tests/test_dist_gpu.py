@@ -65,13 +65,21 @@ def test_allreduced_bucket_equals_sum_of_reference_gradients(C):
     ref_mod = ru.load_ref(C)
     total = {k: 0.0 for k in GRAD_KEYS}
     spread = {k: 0.0 for k in GRAD_KEYS}
+    local_m2d, local_spread = 0.0, 0.0
     for v in range(n_views):
         r = ru.run_impl(ref_mod, scene, cams[v], ups[v], device=str(dev))
         r2 = ru.run_impl(ref_mod, scene, cams[v], ups[v], device=str(dev))
         for k in GRAD_KEYS:
             total[k] = total[k] + r[k].astype(np.float64)
             spread[k] += float(np.abs(r2[k] - r[k]).max())
+        if v in mine:
+            local_m2d = local_m2d + r["dL_dmeans2D"].astype(np.float64)
+            local_spread += float(np.abs(r2["dL_dmeans2D"] - r["dL_dmeans2D"]).max())
+    got = bucket.views["means2D"].cpu().numpy()
+    assert np.abs(got - local_m2d).max() <= REL * np.abs(local_m2d).max() * len(mine) ** 0.5 + 8.0 * local_spread, "means2D (local block)"
     for k in GRAD_KEYS:
+        if k == "dL_dmeans2D":
+            continue  # per-view densification signal: stays local (checked below)
         got = bucket.views[BUCKET_OF[k]].cpu().numpy()
         ref = total[k]
         rel = REL if k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_duncertainty") else 3 * REL
@@ -79,9 +87,9 @@ def test_allreduced_bucket_equals_sum_of_reference_gradients(C):
         err = float(np.abs(got - ref).max())
         assert err <= tol, (k, "rank %d of %d" % (rank, world), err, float(tol))
     if world > 1:
-        # every rank holds the same bucket after the collective
+        # every rank holds the same parameter gradients after the collective
         import torch.distributed as dist
-        mine_sum = bucket.flat.double().sum().reshape(1)
+        mine_sum = bucket.flat[:bucket.reduced_numel].double().sum().reshape(1)
         gathered = [torch.zeros_like(mine_sum) for _ in range(world)]
         dist.all_gather(gathered, mine_sum)
         assert all(torch.equal(g, gathered[0]) for g in gathered)
