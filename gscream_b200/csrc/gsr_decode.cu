@@ -586,6 +586,11 @@ __global__ void compact_visible_kernel(int A, const uint32_t *__restrict__ flags
 	if (i < A && flags[i]) ids[incl[i] - 1] = (uint32_t)i;
 }
 
+// persistent CTAs per SM of the two forward kernels (72 KB of shared memory and 64 registers each: three fit)
+#ifndef GSR_DEC_FWD_CTAS
+#define GSR_DEC_FWD_CTAS 3
+#endif
+
 int sm_count()
 {
 	static int sms = 0;
@@ -650,7 +655,7 @@ cudaError_t decode_stage1(int A, int k, const float *anchor, const float *feat, 
 	a.neural_opacity = neural_opacity; a.mask = mask; a.count = count; a.maskbits = bits;
 	const size_t smem = (size_t)smem_plan(k, false).total * 4;
 	if ((e = set_smem(decode_opacity_kernel, smem)) != cudaSuccess) return e;
-	decode_opacity_kernel<<<grid_for(A, 2), 256, smem, stream>>>(a);
+	decode_opacity_kernel<<<grid_for(A, GSR_DEC_FWD_CTAS), 256, smem, stream>>>(a);
 	count_launch(2);
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if ((e = inclusive_sum_gather(count, nullptr, gincl, A, scratch + L.scan_tmp, stream)) != cudaSuccess) return e;
@@ -666,7 +671,7 @@ cudaError_t decode_stage2(const DecodeArgs &a, cudaStream_t stream)
 	cudaError_t e;
 	const size_t smem = (size_t)smem_plan(a.k, false).total * 4;
 	if ((e = set_smem(decode_outputs_kernel, smem)) != cudaSuccess) return e;
-	decode_outputs_kernel<<<grid_for(a.n_vis, 2), 256, smem, stream>>>(a);
+	decode_outputs_kernel<<<grid_for(a.n_vis, GSR_DEC_FWD_CTAS), 256, smem, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }
