@@ -36,12 +36,19 @@
 // running sum) on entry.
 #include "gsr_blend.cuh"
 #include "gsr_internal.cuh"
+#include <type_traits>
 
 namespace gsr {
 
 constexpr int kWarpsPerCta = GSR_BWD_WARPS_PER_CTA;
 constexpr int kCtasPerTile = kWarpsPerTile / kWarpsPerCta;
 
+__device__ __forceinline__ float exp2_approx(float x)
+{
+	float r;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 // 1 / d for d in [0.01, 1]: MUFU.RCP + one Newton step, no range check (__frcp_rn's slow path is a call behind a branch)
 __device__ __forceinline__ float rcp_1ulp(float d)
 {
@@ -125,6 +132,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, C == 32 ? GSR_BWD32_MINCTAS
 	for (int s = 16; s >= 1; s >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, s));
 	warp_last = min(warp_last, (int)(range.y - range.x));
 	if (warp_last == 0) return; // warps are independent: no barrier follows
+	// ... and the shallowest one (0 when a pixel of the block received nothing at all)
+	int warp_min_last = last_contributor;
+#pragma unroll
+	for (int s = 16; s >= 1; s >>= 1) warp_min_last = min(warp_min_last, __shfl_xor_sync(0xffffffffu, warp_min_last, s));
 
 	// pixel p of the block (p = 8 row + col) -> offset in a plane, or -1 outside the image
 	auto pix_off = [&](int p) -> long long {
@@ -281,26 +292,34 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, C == 32 ? GSR_BWD32_MINCTAS
 		// kSub32 entries at a time: (a) everything that does not depend on the pixel's running state — alpha, 1 / (1 - alpha), G —
 		// then (b) the short carried chain (T, X).  An entry that does not touch the pixel is encoded as alpha = 0, rinv = 1,
 		// G = 0: the recurrence then leaves T unchanged, hands X on unchanged (0 * dot + 1 * X') and produces s = w = 0.
-		uint32_t live = 0; // bit e: some pixel of the warp received gradient from entry e
-		for (int e0 = 0; e0 < m_cur; e0 += kSub32) {
+		bool live = false; // some pixel of the warp received gradient from some entry of the chunk
+		// positions run downwards: once the chunk's first entry lies below every pixel's last contributor, no entry of the
+		// chunk needs the per-pixel position test any more (the common case after the first chunks)
+		const bool below_all = (int)feed.q_pos[feed.done & (kRing - 1)] < warp_min_last;
+		auto sub_batch = [&](int e0, auto check_pos) {
 			float dcol[4] = {0.f, 0.f, 0.f, 0.f};
 			if (kWide) {
 				const float4 d4 = *reinterpret_cast<const float4 *>(s_dot + lane * kDotStride + e0);
 				dcol[0] = d4.x; dcol[1] = d4.y; dcol[2] = d4.z; dcol[3] = d4.w;
 			}
 			float al[kSub32], ri[kSub32], Gs[kSub32], dt[kSub32];
+			bool any_valid = false, near = false;
 #pragma unroll
 			for (int b = 0; b < kSub32; b++) {
 				const int e = e0 + b;
 				const float *ent = ent0 + e * TR::kEntryFloats;
-				const int pos = (int)feed.q_pos[(feed.done + e) & (kRing - 1)]; // 0-based list position
 				const float4 r0 = *reinterpret_cast<const float4 *>(ent);     // x y a b
 				const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4); // c o depth unc
 				const float dx = r0.x - pixf_x, dy = r0.y - pixf_y;
 				const float power = gaussian_power(r0.z, r0.w, r1.x, dx, dy);
-				const float G = expf(power);
+				// G by ex2.approx (2 instructions instead of expf's 8; ~3e-7 relative apart).  The alpha >= 1/255 decision must be the
+				// forward's, which used expf: pairs within 4e-9 of the threshold are redone exactly below.
+				const float G = exp2_approx(power * 1.4426950408889634f);
 				const float alpha = min(0.99f, __fmul_rn(r1.y, G));
-				const bool valid = (e < m_cur) && (pos < last_contributor) && !(power > 0.0f) && !(alpha < kAlphaMin);
+				near = near || fabsf(alpha - kAlphaMin) < 4e-9f;
+				bool valid = (e < m_cur) && !(power > 0.0f) && !(alpha < kAlphaMin);
+				if (decltype(check_pos)::value) valid = valid && (int)feed.q_pos[(feed.done + e) & (kRing - 1)] < last_contributor; // 0-based list position
+				else valid = valid && last_contributor > 0;
 				al[b] = valid ? alpha : 0.f;
 				ri[b] = valid ? rcp_1ulp(__fsub_rn(1.f, alpha)) : 1.f; // T / (1 - alpha) (CR/backward.cu:533) as T * rcp; also serves the background term
 				Gs[b] = valid ? G : 0.f;
@@ -312,8 +331,39 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, C == 32 ? GSR_BWD32_MINCTAS
 					dot += r2.z * grow[0] + r2.w * grow[1 % (kWide ? 1 : C)] + ent[12] * grow[2 % (kWide ? 1 : C)];
 				}
 				dt[b] = valid ? dot : 0.f;
-				if (__any_sync(0xffffffffu, valid)) live |= 1u << e;
+				any_valid = any_valid || valid;
 			}
+			if (__any_sync(0xffffffffu, near)) { // rare: some pair sits at the 1/255 threshold — redo the sub-batch exactly (expf)
+				any_valid = false;
+#pragma unroll 1
+				for (int b = 0; b < kSub32; b++) {
+					const int e = e0 + b;
+					const float *ent = ent0 + e * TR::kEntryFloats;
+					const float4 r0 = *reinterpret_cast<const float4 *>(ent);
+					const float4 r1 = *reinterpret_cast<const float4 *>(ent + 4);
+					const float power = gaussian_power(r0.z, r0.w, r1.x, r0.x - pixf_x, r0.y - pixf_y);
+					const float G = expf(power);
+					const float alpha = min(0.99f, __fmul_rn(r1.y, G));
+					const bool valid = (e < m_cur) && ((int)feed.q_pos[(feed.done + e) & (kRing - 1)] < last_contributor) && !(power > 0.0f) && !(alpha < kAlphaMin);
+					float dot = r1.z * gd + r1.w * gu;
+					if (kWide) dot += s_dot[lane * kDotStride + e];
+					else {
+						const float4 r2 = *reinterpret_cast<const float4 *>(ent + 8);
+						dot += r2.z * grow[0] + r2.w * grow[1 % (kWide ? 1 : C)] + ent[12] * grow[2 % (kWide ? 1 : C)];
+					}
+					// (static indexing keeps the four arrays in registers)
+#pragma unroll
+					for (int bb = 0; bb < kSub32; bb++)
+						if (bb == b) {
+							al[bb] = valid ? alpha : 0.f;
+							ri[bb] = valid ? rcp_1ulp(__fsub_rn(1.f, alpha)) : 1.f;
+							Gs[bb] = valid ? G : 0.f;
+							dt[bb] = valid ? dot : 0.f;
+						}
+					any_valid = any_valid || valid;
+				}
+			}
+			if (__any_sync(0xffffffffu, any_valid)) live = true;
 #pragma unroll
 			for (int b = 0; b < kSub32; b++) {
 				T *= ri[b];
@@ -325,6 +375,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, C == 32 ? GSR_BWD32_MINCTAS
 				last_alpha = al[b];
 				last_dot = dt[b];
 			}
+		};
+		if (below_all) {
+			for (int e0 = 0; e0 < m_cur; e0 += kSub32) sub_batch(e0, std::false_type{});
+		} else {
+			for (int e0 = 0; e0 < m_cur; e0 += kSub32) sub_batch(e0, std::true_type{});
 		}
 		__syncwarp(); // s and w of the chunk are visible to every lane
 
@@ -378,7 +433,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, C == 32 ? GSR_BWD32_MINCTAS
 #pragma unroll
 			for (int r = 0; r < 2; r++) {
 				const int e = gq + 8 * r;
-				const bool on = e < m_cur && ((live >> e) & 1u);
+				const bool on = e < m_cur; // (an entry none of the block's pixels touched adds zeros)
 				const uint32_t id = feed.q_id[(feed.done + e) & (kRing - 1)];
 				if (on && kWide) {
 #pragma unroll
