@@ -8,7 +8,9 @@
 //             into the warp's ring of (Gaussian id, list position) — only entries whose mask names this warp;
 //   gather  : the next 16 ring entries' projected records (and feature rows) are copied into one of the warp's two
 //             private stage buffers with 16-B cp.async (LDGSTS), one chunk ahead of the arithmetic;
-//   blend   : the per-pixel recurrence runs over the landed chunk, entries in order, operands broadcast from shared memory.
+//   blend   : the landed 16-entry chunk is processed in phases: the per-pixel recurrence (lane = pixel, entries in order) on the
+//             FP32 pipe, the dense per-(block, chunk) products at C = 32 as 3xTF32 mma.sync on the tensor pipe (helpers below;
+//             gsr_blend_fwd.cu / gsr_blend_bwd.cu).
 // v1 staged every instance of the tile once per CTA behind a per-round __syncthreads(); ncu showed 18-19 % of the warp
 // samples waiting at that barrier for the slowest warp of the round (profiles/r1_blend_v3_summary.md).  v2 trades ~1.4x more
 // L2->SM gather traffic (an instance is fetched by each warp that needs it) for fully decoupled warps, a per-warp early

@@ -16,18 +16,18 @@
 //   * Every term the reference adds atomically is linear in two per-(pixel, Gaussian) scalars,
 //         s = G * dL_dalpha      and      w = alpha * T,
 //     with coefficients that depend only on the Gaussian's record and the pixel's position / gradient row.  A warp
-//     therefore works on a landed chunk of its feed (gsr_blend.cuh) in two phases:
-//       phase 1 (lane = pixel, sequential in depth): the recurrence; leaves s and w of every (entry, pixel) of the chunk
-//                in 4 KB of shared memory.  Nothing in it waits for a reduction.
-//       phase 2 (entries independent): the per-Gaussian sums over the warp's 32 pixels.  The 8 geometric / scalar terms are
-//                rebuilt from s, w and the staged record and reduced by a transpose-reduce butterfly over TWO entries at a
-//                time (16 shuffles per pair, the first level free of selects because the upper half-warp loads the pair
-//                swapped); the C = 32 colour terms by switching roles — lane l owns channel l and holds the gradient COLUMN
-//                of the warp's 32 pixels in registers — ending in one coalesced 128-B red.global.add per (warp, Gaussian)
-//                where the reference issues 32 x C scalar atomics.
-//     Round 1 ran both per entry, the butterfly's 9 dependent shuffles and the colour sums' FMA chain on the recurrence's
-//     critical path: 63 % issue-slot utilisation at 16 warps per SM (profiles/r1_blend_v7_summary.md).  Separating the phases
-//     lets ptxas interleave independent entries' chains (profiles/r2_blend_bwd.md).
+//     therefore works on a landed 16-entry chunk of its feed (gsr_blend.cuh) in phases:
+//       phase 0 (C = 32): dot[p][e] = g_p . f_e for the whole chunk as one [32 x 32] x [32 x 16] product on the tensor pipe;
+//       phase 1 (lane = pixel, sequential in depth): the recurrence, branch-free, four entries side by side; leaves s and w
+//                of every (entry, pixel) of the chunk in 4 KB of shared memory.  Nothing in it waits for a reduction;
+//       phase 2 (entries independent): every per-Gaussian sum over the warp's 32 pixels as tensor-pipe products of the s / w
+//                tiles with operands that are fixed per warp — the gradient block (colour sums), the depth / uncertainty
+//                gradients, and the monomials of the block-centred pixel coordinates (the geometric terms as moments) —
+//                ending in red.global.add.v2.f32 straight from the accumulator fragments, 10 per chunk, where the reference
+//                issues 32 x (C + 8) scalar atomics per (warp, Gaussian).
+//     Details and the measurements that led here (round 1: everything per entry on the FP32 pipe, a 9-shuffle butterfly on
+//     the recurrence's critical path; then the shared-memory data-pipe finding) are with the kernel below and in
+//     profiles/r2_blend_mma.md.
 //   * Same warp-private feed as the forward kernel (per-warp list scan by the instance masks, private double-buffered
 //     cp.async gather, no block barrier), run back to front and started at the warp's own deepest last contributor.
 //
