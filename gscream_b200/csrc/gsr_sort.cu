@@ -77,8 +77,12 @@ __global__ void __launch_bounds__(kRsThreads) rs_offsets_kernel(uint32_t *__rest
 	}
 }
 
+// resident CTAs per SM asked of ptxas: two (no spill with the kept ranks); three spill 72 B and are 10 % slower
+#ifndef GSR_RS_MINCTAS
+#define GSR_RS_MINCTAS 2
+#endif
 // stable scatter of one digit pass
-__global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+__global__ void __launch_bounds__(kRsThreads, GSR_RS_MINCTAS) rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                                                                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_cap,
                                                                 const uint32_t *__restrict__ n_dev, int shift, int width,
                                                                 const uint32_t *__restrict__ offsets, int tiles)
@@ -121,13 +125,20 @@ __global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(const uint32_
 		}
 		return m;
 	};
-	// pass A: this warp's digit counts (the lowest lane of every peer group adds the group size)
+	// pass A: this warp's digit counts (the lowest lane of every peer group adds the group size).  Each element's rank inside
+	// its peer group and the group's size are kept (two 16-bit fields per register pair of elements) so that pass B does not
+	// have to rebuild the peer masks: `width` ballots per element once instead of twice.
+	uint32_t rank_cnt[kRsItems / 2];
+#pragma unroll
+	for (int i = 0; i < kRsItems / 2; i++) rank_cnt[i] = 0;
 #pragma unroll
 	for (int i = 0; i < kRsItems; i++) {
 		const bool valid = run_base + i * 32 + lane < n;
 		const uint32_t d = (key[i] >> shift) & mask;
 		const uint32_t m = peers_of(d, valid);
-		if (valid && (m & lt_mask) == 0) s_hist[warp][d] += __popc(m); // one writer per (warp, digit) per step
+		const uint32_t r = __popc(m & lt_mask), c = __popc(m);
+		if (valid && r == 0) s_hist[warp][d] += c; // one writer per (warp, digit) per step
+		rank_cnt[i >> 1] |= (r | (c << 8)) << (16 * (i & 1));
 		__syncwarp();
 	}
 	__syncthreads();
@@ -147,19 +158,18 @@ __global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(const uint32_
 	for (int w = 0; w < 8; w++) s_hist[w][t] += tile_start; // s_hist[w][d] = next free slot of (warp w, digit d) in the tile
 	__syncthreads();
 
-	// pass B: same peer groups again, now handing out slots in input order; reorder through shared memory so that equal
+	// pass B: the same peer groups, now handing out slots in input order; reorder through shared memory so that equal
 	// digits are contiguous
 #pragma unroll
 	for (int i = 0; i < kRsItems; i++) {
 		const bool valid = run_base + i * 32 + lane < n;
 		const uint32_t d = (key[i] >> shift) & mask;
-		const uint32_t m = peers_of(d, valid);
+		const uint32_t rc = (rank_cnt[i >> 1] >> (16 * (i & 1))) & 0xFFFFu, r = rc & 0xFFu, c = rc >> 8;
 		uint32_t slot = 0;
 		if (valid) slot = s_hist[warp][d];
 		__syncwarp();
 		if (valid) {
-			const uint32_t r = __popc(m & lt_mask);
-			if (r == 0) s_hist[warp][d] = slot + __popc(m);
+			if (r == 0) s_hist[warp][d] = slot + c;
 			s_keys[slot + r] = key[i];
 			s_vals[slot + r] = val[i];
 		}
