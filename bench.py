@@ -376,7 +376,7 @@ def run_ours(args, cfg, rank, world, local):
         peak, peak_src = _peaks()
         bytes_bwd = algorithmic_bytes_blend_backward(C, W, H, R, V)
         t_bwd = stage_ms_rank0["blend_backward"]
-        bwd_kernel = "gsr::blend_backward_c32_kernel" if C == 32 else "gsr::blend_backward_kernel<%d>" % C
+        bwd_kernel = "gsr::blend_backward_kernel<%d>" % C
         traffic, traffic_src = _measured_traffic(bwd_kernel + ":" + args.workload) if args.scale_mult == 1.0 else (None, None)
         achieved = bytes_bwd / (t_bwd * 1e-3) / 1e9 if t_bwd else None
         out = {
