@@ -183,8 +183,8 @@ def run_ours(args, cfg, rank, world, local):
     info = {}
 
     def step():
-        bucket.zero_()
-        outs = render_views_into_bucket(scene, [cam], ups, bucket, keep_outputs=True)
+        # (no bucket.zero_(): the first view's backward overwrites the bucket, gscream_b200/dist.py)
+        outs = render_views_into_bucket(scene, [cam], ups, bucket, keep_outputs=True, overwrite=True)
         info["R"] = outs[0][4]
         info["radii"] = outs[0][3]
         allreduce_bucket(bucket)

@@ -81,8 +81,10 @@ def allreduce_bucket(bucket: GradBucket, group=None, average: bool = False):
 
 
 def render_views_into_bucket(scene: Dict[str, torch.Tensor], cameras: Sequence[dict], upstream: Sequence[tuple],
-                             bucket: GradBucket, keep_outputs: bool = False):
+                             bucket: GradBucket, keep_outputs: bool = False, overwrite: bool = False):
     """Forward + backward of every local view, gradients accumulated into `bucket` (not zeroed here).
+    overwrite=True: the first view's backward OVERWRITES the bucket (the kernels write every element, zeros for culled
+    Gaussians) and only the later views add to it, so the caller need not zero 4 * (15 + C) * P bytes per step.
 
     scene: device tensors means3D/colors/opacities/uncertainties/scales/rotations/bg;
     cameras: dicts as produced by scenes.make_camera with device matrices;
@@ -93,7 +95,7 @@ def render_views_into_bucket(scene: Dict[str, torch.Tensor], cameras: Sequence[d
     outs = []
     empty = torch.empty(0)
     out_map = bucket.as_backward_out()
-    for cam, (gc, gd, gu) in zip(cameras, upstream):
+    for i, (cam, (gc, gd, gu)) in enumerate(zip(cameras, upstream)):
         R, color, depth, unc, radii, geom, binning, img = _C.rasterize_gaussians(
             scene["bg"], scene["means3D"], scene["colors"], scene["opacities"], scene["uncertainties"], scene["scales"],
             scene["rotations"], 1.0, empty, cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"],
@@ -101,7 +103,7 @@ def render_views_into_bucket(scene: Dict[str, torch.Tensor], cameras: Sequence[d
         _C.rasterize_gaussians_backward(
             scene["bg"], scene["means3D"], radii, scene["colors"], scene["scales"], scene["rotations"], 1.0, empty,
             cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], gc, gd, gu, empty, 1, cam["campos"],
-            geom, R, binning, img, False, out=out_map, accumulate=True, want_cov3D=False)
+            geom, R, binning, img, False, out=out_map, accumulate=not (overwrite and i == 0), want_cov3D=False)
         if keep_outputs:
             outs.append((color, depth, unc, radii, R))
     return outs

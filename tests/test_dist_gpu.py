@@ -56,8 +56,9 @@ def test_allreduced_bucket_equals_sum_of_reference_gradients(C):
     s = {k: v.to(dev) for k, v in scene.items()}
     mine = shard_views(n_views, world, rank)
     bucket = GradBucket(P, C, device=dev)
+    bucket.flat.fill_(123.0)   # stale contents: overwrite=True must not need a zeroed bucket
     render_views_into_bucket(s, [{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in cams[v].items()} for v in mine],
-                             [tuple(t.to(dev) for t in ups[v]) for v in mine], bucket)
+                             [tuple(t.to(dev) for t in ups[v]) for v in mine], bucket, overwrite=True)
     allreduce_bucket(bucket)
     torch.cuda.synchronize()
 

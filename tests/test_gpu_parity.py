@@ -168,10 +168,12 @@ ORACLE_KEY = {"dL_dmeans3D": "dL_dmeans3D", "dL_dmeans2D": "dL_dmean2D", "dL_dco
     (40, 1, 1, 32, 109, 8.0, 0.0),
     (2500, 333, 1, 32, 110, 3.0, 0.0),
     (1200, 19, 45, 3, 111, 9.0, 5.0),
+    (2500, 150, 90, 32, 112, 2.5, -4.0),     # C = 32 with a non-zero background
 ])
 def test_against_cpu_oracle(P, W, H, C, seed, smult, yaw):
     _require_native()
-    scene = scenes.make_scene(P, W, H, C, seed, scale_mult=smult, bg_value=0.2 if C == 3 else 0.0)
+    # (seed 112: a 32-channel scene WITH a background — the backward's background term takes its own path at C = 32)
+    scene = scenes.make_scene(P, W, H, C, seed, scale_mult=smult, bg_value=0.2 if C == 3 else (0.15 if seed == 112 else 0.0))
     cam = scenes.make_camera(W, H, yaw_deg=yaw)
     grads = scenes.make_upstream_grads(C, W, H, seed)
     m = ru.run_impl(ours, scene, cam, grads)
