@@ -54,7 +54,21 @@ __global__ void __launch_bounds__(kRsThreads) rs_histogram_kernel(const uint32_t
 	__syncthreads();
 	const uint32_t c = s_hist[t];
 	counts[(size_t)t * tiles + blockIdx.x] = c;
-	if (c) atomicAdd(&totals[t], c);
+	// digit totals: by atomics for small inputs; above kRsTotalsByRows tiles they serialise at L2 (thousands of adds per
+	// address: 50 us at 10^4 tiles) and rs_totals_kernel sums the rows instead
+	if (totals && c) atomicAdd(&totals[t], c);
+}
+
+// one CTA per digit: totals[digit] = sum over tiles of counts[digit][tile]  (large inputs only)
+__global__ void __launch_bounds__(kRsThreads) rs_totals_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ totals, int tiles)
+{
+	__shared__ uint32_t s_warp[8];
+	const uint32_t *row = counts + (size_t)blockIdx.x * tiles;
+	uint32_t sum = 0;
+	for (int i = threadIdx.x; i < tiles; i += kRsThreads) sum += row[i];
+	uint32_t tot;
+	block_exclusive_scan_256(sum, s_warp, &tot);
+	if (threadIdx.x == 0) totals[blockIdx.x] = tot;
 }
 
 // one CTA per digit: counts[digit][tile] <- global base of the digit + exclusive prefix over tiles
@@ -67,12 +81,20 @@ __global__ void __launch_bounds__(kRsThreads) rs_offsets_kernel(uint32_t *__rest
 	block_exclusive_scan_256(t < d ? totals[t] : 0u, s_warp, &base);
 	uint32_t *row = counts + (size_t)d * tiles;
 	uint32_t carry = base;
-	for (int c0 = 0; c0 < tiles; c0 += kRsThreads) {
-		const int i = c0 + t;
-		const uint32_t v = i < tiles ? row[i] : 0u;
+	// four consecutive tiles per thread and round: a quarter of the block scans (each costs two barriers)
+	for (int c0 = 0; c0 < tiles; c0 += 4 * kRsThreads) {
+		const int i = c0 + 4 * t;
+		uint32_t v[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) v[j] = i + j < tiles ? row[i + j] : 0u;
 		uint32_t tot;
-		const uint32_t ex = block_exclusive_scan_256(v, s_warp, &tot);
-		if (i < tiles) row[i] = carry + ex;
+		const uint32_t ex = block_exclusive_scan_256(v[0] + v[1] + v[2] + v[3], s_warp, &tot);
+		uint32_t run = carry + ex;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			if (i + j < tiles) row[i + j] = run;
+			run += v[j];
+		}
 		carry += tot;
 	}
 }
@@ -216,7 +238,12 @@ int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint3
 	for (int p = 0; p < pl.passes; p++) {
 		const int width = std::min(8, bits - 8 * p);
 		const uint32_t mask = (1u << width) - 1u;
-		rs_histogram_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, n, n_dev, 8 * p, mask, pl.tiles, counts, totals + p * 256);
+		const bool by_rows = pl.tiles > kRsTotalsByRows;
+		rs_histogram_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, n, n_dev, 8 * p, mask, pl.tiles, counts, by_rows ? nullptr : totals + p * 256);
+		if (by_rows) {
+			rs_totals_kernel<<<256, kRsThreads, 0, stream>>>(counts, totals + p * 256, pl.tiles);
+			count_launch();
+		}
 		rs_offsets_kernel<<<256, kRsThreads, 0, stream>>>(counts, totals + p * 256, pl.tiles);
 		rs_scatter_kernel<<<pl.tiles, kRsThreads, 0, stream>>>(kin, vin, kout, vout, n, n_dev, 8 * p, width, counts, pl.tiles);
 		count_launch(3);

@@ -24,6 +24,7 @@ constexpr int kRsThreads = 256;
 constexpr int kRsItems = 16;
 constexpr int kRsTile = kRsThreads * kRsItems; // 4096
 constexpr int kRsMaxPasses = 4;
+constexpr int kRsTotalsByRows = 1024; // above this many tiles the digit totals are row sums, not atomics
 
 struct RadixPlan {
 	int passes;       // ceil(bits / 8)
