@@ -417,30 +417,36 @@ def run_ours(args, cfg, rank, world, local):
 
 def other_configs():
     """The other BASELINE.json configurations, measured by this same run so that they are driver-run numbers too: config2
-    (configs[1]) and the config4 substitute (configs[3]), each with both arms.  One child process per arm; device
-    timed like the main line; a few seconds each."""
+    (configs[1]), the config4 substitute (configs[3]) and SURVEY 8d's heavy variant of config3, each with both arms.
+    One child process per arm; device timed like the main line; a few seconds each."""
     res = {}
-    for wl, steps in (("config2", 40), ("config4", 20)):
+    for name, wl, steps, extra in (("config2", "config2", 40, []), ("config4", "config4", 20, []),
+                                   ("config3_heavy", "config3", 20, ["--scale-mult", "3.0", "--value-only"])):
         for impl in ("ours", "reference"):
             cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--impl", impl, "--steps", str(steps), "--warmup", "5",
-                   "--no-cpu-baseline", "--no-other-configs"]
+                   "--no-cpu-baseline", "--no-other-configs"] + extra
             try:
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
                 d = json.loads(r.stdout.strip().splitlines()[-1])
                 if "unavailable" in d:
-                    res.setdefault(wl, {})[impl] = {"unavailable": d["unavailable"]}
+                    res.setdefault(name, {})[impl] = {"unavailable": d["unavailable"]}
                     continue
-                e = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "workload": d["config"]["workload"]}
+                e = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"]}
+                if "config" in d:
+                    e["workload"] = d["config"]["workload"]
+                if "num_rendered" in d:
+                    e["num_rendered"] = d["num_rendered"]
                 if "stage_ms" in d:
                     e["stage_ms"] = d["stage_ms"]
                 if "e2e_device_resident_api" in d:
                     e["device_resident_api"] = d["e2e_device_resident_api"]["value"]
-                res.setdefault(wl, {})[impl] = e
+                res.setdefault(name, {})[impl] = e
             except Exception as ex:  # a failed extra must not lose the main line
-                res.setdefault(wl, {})[impl] = {"error": repr(ex)[:200]}
-        a, b = res[wl].get("ours", {}), res[wl].get("reference", {})
+                res.setdefault(name, {})[impl] = {"error": repr(ex)[:200]}
+        a, b = res[name].get("ours", {}), res[name].get("reference", {})
         if "value" in a and "value" in b:
-            res[wl]["ratio"] = a["value"] / b["value"]
+            res[name]["ratio"] = a["value"] / b["value"]
+    res["config3_heavy"]["note"] = "config3 with the splat scale x3 (SURVEY 8d's 'heavy' variant: ~40 tile instances per Gaussian, as real scenes have); device-resident bucket path vs the reference's device-resident arm"
     return res
 
 

@@ -180,3 +180,35 @@ def test_ctypes_prototypes_match_header_declarations():
         assert len(plist) == len(bound), (name, len(plist), len(bound))
         for i, (p, b) in enumerate(zip(plist, bound)):
             assert ctype_of(p) is b, "%s argument %d (%s): header says %s, ctypes binds %s" % (name, i, p.strip(), ctype_of(p).__name__, b.__name__)
+
+
+def test_binning_buffer_describes_itself(lib):
+    """The binning buffer's layout follows from its byte size (gsr_binning_capacity is the inverse of gsr_binning_bytes), so a
+    buffer sized from an ESTIMATE of num_rendered is laid out identically by forward, backward and export."""
+    for (P, W, H) in ((1000, 64, 64), (10 ** 6, 1920, 1080), (5 * 10 ** 5, 1008, 567), (7, 1, 1)):
+        prev_bytes = 0
+        for R in (1, 2, 4095, 4096, 4097, 10 ** 5, 7302277, 4 * 10 ** 7):
+            nbytes = lib.gsr_binning_bytes(P, R, W, H)
+            assert nbytes >= prev_bytes            # monotone in the instance count
+            prev_bytes = nbytes
+            cap = lib.gsr_binning_capacity(P, W, H, nbytes)
+            assert cap >= R                        # a buffer sized for R holds R ...
+            assert lib.gsr_binning_bytes(P, cap, W, H) <= nbytes        # ... cap's own layout fits ...
+            assert lib.gsr_binning_bytes(P, cap + 1, W, H) > nbytes     # ... and cap is the largest such count
+        assert lib.gsr_binning_capacity(P, W, H, 0) == 0 and lib.gsr_binning_capacity(P, W, H, 100) == 0
+
+
+def test_capacity_estimate_policy():
+    """gscream_b200._C sizes the binning buffer before num_rendered reaches the host: no history -> exact path; afterwards 25 %
+    above a slowly decaying running maximum."""
+    from gscream_b200 import _C
+    key = ("test-device", 123, 45, 67)
+    _C._R_HINT.pop(key, None)
+    assert _C._capacity_guess(key) is None
+    _C._capacity_update(key, 1000)
+    assert _C._capacity_guess(key) == int(1000 * 1.25) + 65536
+    _C._capacity_update(key, 10)                       # a much smaller view: the maximum decays by 2 % per call, not at once
+    assert _C._R_HINT[key] == pytest.approx(980.0)
+    _C._capacity_update(key, 5000)                     # a larger one takes over immediately
+    assert _C._R_HINT[key] == 5000.0
+    _C._R_HINT.pop(key, None)
