@@ -267,6 +267,9 @@ def run_ours(args, cfg, rank, world, local):
             means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], uncertainties=leaves["uncertainties"],
             colors_precomp=leaves["colors"], scales=leaves["scales"], rotations=leaves["rotations"])
         torch.autograd.backward((color, depth, unc), tuple(sl["g"]))
+        if world > 1:
+            for k in keys:
+                dist.all_reduce(leaves[k].grad, op=dist.ReduceOp.SUM)
         loss = (color.detach() * sl["g"][0]).sum() + leaves["means3D"].grad.abs().sum()
         loss_host.copy_(loss.reshape(1), non_blocking=True)                 # the step's result goes back to the host
         for k in keys:
@@ -323,6 +326,9 @@ def run_ours(args, cfg, rank, world, local):
                 means3D=res["means3D"], means2D=m2d_res, opacities=res["opacities"], uncertainties=res["uncertainties"],
                 colors_precomp=res["colors"], scales=res["scales"], rotations=res["rotations"])
             torch.autograd.backward((color, depth, unc), tuple(sl["g"]))
+            if world > 1:   # the step's collective, through the public API: the parameter gradients of all ranks are summed
+                for k in keys:
+                    dist.all_reduce(res[k].grad, op=dist.ReduceOp.SUM)
             loss = (color.detach() * sl["g"][0]).sum() + res["means3D"].grad.abs().sum()
             loss_host.copy_(loss.reshape(1), non_blocking=True)
             for t in list(res.values()) + [m2d_res]:
@@ -351,6 +357,9 @@ def run_ours(args, cfg, rank, world, local):
         color, depth, unc, radii = rast_res(means3D=res["means3D"], means2D=m2d_res, opacities=res["opacities"], uncertainties=res["uncertainties"],
                                             shs=None, colors_precomp=res["colors"], scales=res["scales"], rotations=res["rotations"], cov3D_precomp=None)
         torch.autograd.backward((color, depth, unc), ups[0])
+        if world > 1:
+            for k in keys:
+                dist.all_reduce(res[k].grad, op=dist.ReduceOp.SUM)
         for t in list(res.values()) + [m2d_res]:
             t.grad = None
 
@@ -390,7 +399,7 @@ def run_ours(args, cfg, rank, world, local):
                        "l2": "working set (features 128 MB + records 64 MB + planes 282 MB x2) exceeds the 126 MB L2; no explicit flush",
                        "collective": ("1 NCCL sum-allreduce of the %.0f MB parameter-gradient bucket per step (the per-view means2D block stays local)" % (bucket.reduced_nbytes() / 1e6)) if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": 4,
-                    "note": "public GaussianRasterizer API + torch.autograd.backward; per step the camera (view / projection matrices, position) is copied from pinned host memory (double-buffered on a copy stream) and a result scalar is read back.  The Gaussian arrays are resident like model weights and so is the view's supervision (the upstream-gradient planes), as in GScream, whose cameras keep every view's images on the GPU (scene/cameras.py) — the reference arm is timed with everything resident as well.  The rendered planes are NOT copied back: their consumer (the loss) lives on the device.  Round 1 reported the supervision-from-host form under this key; it is kept below"},
+                    "note": "public GaussianRasterizer API + torch.autograd.backward (at N > 1 followed by the all-reduce of the six parameter-gradient tensors, 176 MB at config3); per step the camera (view / projection matrices, position) is copied from pinned host memory (double-buffered on a copy stream) and a result scalar is read back.  The Gaussian arrays are resident like model weights and so is the view's supervision (the upstream-gradient planes), as in GScream, whose cameras keep every view's images on the GPU (scene/cameras.py) — the reference arm is timed with everything resident as well.  The rendered planes are NOT copied back: their consumer (the loss) lives on the device.  Round 1 reported the supervision-from-host form under this key; it is kept below"},
             "e2e_supervision_from_host": {"value": e2e_sup_value, "unit": "views/s", "h2d_bytes_per_step": h2d_view_bytes, "d2h_bytes_per_step": 4,
                     "note": "as e2e, but the view's upstream-gradient planes (C colour + depth + uncertainty: 282 MB at config3) are copied from pinned host memory every step as well: a measurement of the PCIe link (~56 GB/s), not of the kernels"},
             "e2e_device_resident_api": {"value": api_value, "unit": "views/s", "ms_per_step": api_ms / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
