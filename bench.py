@@ -81,13 +81,13 @@ class ClockSampler:
 
 def _measured_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the `ncu --set full` capture recorded in
-    profiles/traffic.json — valid only for the library build it was captured from (keyed by the build digest of the sources +
-    flags, gscream_b200/_build.py); any other build reports null rather than a stale constant."""
+    profiles/traffic.json — valid only for the kernel build it was captured from (keyed by the digest of the blend kernels'
+    sources + compiler flags, gscream_b200/_build.blend_digest); any other build reports null rather than a stale constant."""
     try:
         from gscream_b200 import _build
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             table = json.load(fh)
-        entry = table.get(_build._digest(), {}).get(kernel)
+        entry = table.get(_build.blend_digest(), {}).get(kernel)
         return (int(entry["dram_bytes"]), entry.get("source")) if entry else (None, None)
     except Exception:
         return None, None

@@ -24,13 +24,22 @@ FLAGS = [
 ] + os.environ.get("GSR_EXTRA_NVCC_FLAGS", "").split()
 
 
-def _digest():
+def _digest(files=None):
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS:
+    for f in (SOURCES + HEADERS) if files is None else files:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
+
+
+# the sources (and compiler flags) that determine the blend kernels' machine code: profiles/traffic.json keys its ncu captures
+# of those kernels by this digest
+BLEND_FILES = ["gsr_blend_fwd.cu", "gsr_blend_bwd.cu", "gsr_blend.cuh", "gsr_common.cuh", "gsr_internal.cuh"]
+
+
+def blend_digest():
+    return _digest(BLEND_FILES)
 
 
 def is_fresh():
