@@ -144,7 +144,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, uncertaintys, scal
                 img.data_ptr(), img.numel(), out_color.data_ptr(), out_depth.data_ptr(), out_unc.data_ptr(), stream))
             return buf
 
-        key = (dev.index, P, W, H)
+        # history per device, image size and magnitude of P: in training P changes a little every iteration (the kept offsets),
+        # num_rendered follows it smoothly, and the table must not grow by one entry per distinct P
+        key = (dev.index, P.bit_length(), W, H)
         guess = None if os.environ.get("GSR_EXACT_BINNING") else _capacity_guess(key)
         binning = second_half(-1, guess) if guess is not None else None
         counted.synchronize()

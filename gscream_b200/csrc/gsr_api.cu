@@ -381,10 +381,24 @@ int gsr_decode_stage2(int A, int feat_dim, int n_offsets, int64_t n_vis, int64_t
                       float *out_scaling, float *rot, gsr_stream_t stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
+	// n_vis == -1: the counts of stage 1 have not reached the host yet.  The kernel then reads n_vis from the scratch buffer
+	// (stage 1 ran with a visibility mask and left the visible list there) and P is the CAPACITY of the six outputs, which
+	// A * n_offsets rows always satisfy; the caller narrows them once the counts are in.
+	const bool counts_on_device = n_vis == -1;
+	if (counts_on_device) {
+		if (A <= 0 || P < (int64_t)A * n_offsets) return A == 0 ? 0 : GSR_E_BADARG;
+		n_vis = A; // grid and validation bound; P <= n_vis * n_offsets holds with equality
+		P = (int64_t)A * n_offsets;
+	}
 	if (A == 0 || n_vis == 0 || P == 0) return (A < 0 || n_vis < 0 || P < 0) ? GSR_E_BADARG : 0;
 	DecodeArgs a{};
 	const int rc = fill_decode_args(a, A, feat_dim, n_offsets, n_vis, P, anchor, anchor_feat, offset, scaling, campos, mlp_params, scratch, scratch_bytes);
 	if (rc) return rc;
+	if (counts_on_device) {
+		const DecodeLayout L = decode_layout(A);
+		a.vis_ids = (const uint32_t *)((char *)scratch + L.vis_ids);
+		a.n_vis_dev = (const uint32_t *)((char *)scratch + L.vis_incl) + (A - 1);
+	}
 	if (!neural_opacity || !xyz || !color || !opacity || !uncertainty || !out_scaling || !rot) return GSR_E_BADARG;
 	a.neural_opacity = const_cast<float *>(neural_opacity);
 	a.out_xyz = xyz; a.out_color = color; a.out_opacity = opacity; a.out_uncertainty = uncertainty; a.out_scaling = out_scaling; a.out_rot = rot;

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a)
 	float *X4 = sm + pl.warp0 + warp * pl.per_warp + pl.x4;
 	float *H4 = sm + pl.warp0 + warp * pl.per_warp + pl.h4;
 	float *OUT4 = sm + pl.warp0 + warp * pl.per_warp + pl.out4;
-	const int n_vis = a.n_vis;
+	const int n_vis = a.n_vis_dev ? (int)*a.n_vis_dev : a.n_vis; // (device copy when the host has not read the counts yet)
 	const int groups = (n_vis + kNA - 1) / kNA;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
 	GroupRaw raw;

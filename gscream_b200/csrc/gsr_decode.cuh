@@ -21,7 +21,7 @@ DecodeLayout decode_layout(int A);
 struct DecodeArgs {
 	int k;                       // n_offsets
 	int n_vis;                   // visible anchors (host value; upper bound A in stage 1)
-	const uint32_t *n_vis_dev;   // stage 1 only: device copy of n_vis (null: n_vis is exact)
+	const uint32_t *n_vis_dev;   // device copy of n_vis (null: n_vis is exact); stage 1, and stage 2 when launched before the host read the counts
 	const uint32_t *vis_ids;     // [n_vis] visible anchor indices, ascending (null: identity)
 	const float *anchor, *feat, *offset, *scaling, *campos;
 	DecodeWeights wt;

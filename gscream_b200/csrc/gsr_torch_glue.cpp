@@ -74,16 +74,18 @@ int64_t *pinned_counter(int device)
 // running maximum of what this problem shape produced so far; -1: no history yet
 std::mutex g_hint_mu;
 std::map<std::tuple<int, int, int, int>, double> g_hint;
+// (keyed by the magnitude of P, not P itself: in training P changes a little every iteration and num_rendered follows it smoothly)
+int magnitude(int P) { int b = 0; while (P > 0) { b++; P >>= 1; } return b; }
 int64_t capacity_guess(int device, int P, int W, int H)
 {
 	std::lock_guard<std::mutex> lock(g_hint_mu);
-	auto it = g_hint.find(std::make_tuple(device, P, W, H));
+	auto it = g_hint.find(std::make_tuple(device, magnitude(P), W, H));
 	return it == g_hint.end() ? -1 : (int64_t)(it->second * 1.25) + 65536;
 }
 void capacity_update(int device, int P, int W, int H, int64_t R)
 {
 	std::lock_guard<std::mutex> lock(g_hint_mu);
-	double &h = g_hint[std::make_tuple(device, P, W, H)];
+	double &h = g_hint[std::make_tuple(device, magnitude(P), W, H)];
 	h = std::max((double)R, 0.98 * h);
 }
 

@@ -98,18 +98,27 @@ class _DecodeAnchors(torch.autograd.Function):
             _lib.check(lib.gsr_decode_stage1(A, feat_dim, k, anchor.data_ptr(), feat.data_ptr(), vm.data_ptr() if vm is not None else None,
                                              campos.data_ptr(), params, scratch.data_ptr(), scratch.numel(), nop_full.data_ptr(),
                                              mask_full.data_ptr(), counts.data_ptr(), stream))
-            torch.cuda.current_stream().synchronize()   # the one host sync: output sizes are data dependent
+            # Output sizes are data dependent (the reference syncs on every boolean index).  The counts travel to a pinned
+            # buffer behind stage 1; stage 2 is launched right away into outputs with the capacity of all A * k offsets (with a
+            # visibility mask it reads n_vis from device memory), and the host waits on an EVENT behind the counts only — the
+            # GPU keeps running stage 2 — before narrowing the outputs to their first P rows.
+            counted = torch.cuda.Event()
+            counted.record()
+            cap = A * k
+            xyz = torch.empty(cap, 3, dtype=torch.float32, device=dev)
+            color = torch.empty(cap, 3, dtype=torch.float32, device=dev)
+            opacity = torch.empty(cap, 1, dtype=torch.float32, device=dev)
+            uncertainty = torch.empty(cap, 1, dtype=torch.float32, device=dev)
+            out_scaling = torch.empty(cap, 3, dtype=torch.float32, device=dev)
+            rot = torch.empty(cap, 4, dtype=torch.float32, device=dev)
+            if cap > 0:
+                _lib.check(lib.gsr_decode_stage2(A, feat_dim, k, -1 if vm is not None else A, cap, anchor.data_ptr(), feat.data_ptr(),
+                                                 offset.data_ptr(), scaling.data_ptr(), campos.data_ptr(), params, scratch.data_ptr(),
+                                                 scratch.numel(), nop_full.data_ptr(), xyz.data_ptr(), color.data_ptr(), opacity.data_ptr(),
+                                                 uncertainty.data_ptr(), out_scaling.data_ptr(), rot.data_ptr(), stream))
+            counted.synchronize()
             n_vis, P = int(counts[0]), int(counts[1])
-            xyz = torch.empty(P, 3, dtype=torch.float32, device=dev)
-            color = torch.empty(P, 3, dtype=torch.float32, device=dev)
-            opacity = torch.empty(P, 1, dtype=torch.float32, device=dev)
-            uncertainty = torch.empty(P, 1, dtype=torch.float32, device=dev)
-            out_scaling = torch.empty(P, 3, dtype=torch.float32, device=dev)
-            rot = torch.empty(P, 4, dtype=torch.float32, device=dev)
-            _lib.check(lib.gsr_decode_stage2(A, feat_dim, k, n_vis, P, anchor.data_ptr(), feat.data_ptr(), offset.data_ptr(),
-                                             scaling.data_ptr(), campos.data_ptr(), params, scratch.data_ptr(), scratch.numel(),
-                                             nop_full.data_ptr(), xyz.data_ptr(), color.data_ptr(), opacity.data_ptr(),
-                                             uncertainty.data_ptr(), out_scaling.data_ptr(), rot.data_ptr(), stream))
+            xyz, color, opacity, uncertainty, out_scaling, rot = (t[:P] for t in (xyz, color, opacity, uncertainty, out_scaling, rot))
         neural_opacity = nop_full[:n_vis * k].view(-1, 1)
         mask = mask_full[:n_vis * k]
         ctx.save_for_backward(anchor, feat, offset, scaling, campos, scratch, *mlp)

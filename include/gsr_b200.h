@@ -183,7 +183,10 @@ GSR_API int gsr_decode_stage1(
     const float *const *mlp_params, void *scratch, size_t scratch_bytes,
     float *neural_opacity, uint8_t *mask, int64_t *counts_host, gsr_stream_t stream);
 /* Stage 2: xyz[P,3] color[P,3] opacity[P] uncertainty[P] out_scaling[P,3] rot[P,4] of the kept offsets, in
- * (visible anchor, offset) order — gaussian_renderer/__init__.py:66-101. */
+ * (visible anchor, offset) order — gaussian_renderer/__init__.py:66-101.
+ * n_vis == -1: stage 1 ran with a visibility mask and its counts have not reached the host yet; the kernel reads n_vis from the
+ * scratch buffer and P is the CAPACITY (rows) of the six outputs, at least A * n_offsets.  The caller launches this right behind
+ * stage 1, waits for the counts only, and narrows the outputs to their first P rows. */
 GSR_API int gsr_decode_stage2(
     int A, int feat_dim, int n_offsets, int64_t n_vis, int64_t P,
     const float *anchor, const float *anchor_feat, const float *offset, const float *scaling, const float *campos,
