@@ -429,10 +429,12 @@ def other_configs():
     (configs[1]), the config4 substitute (configs[3]) and SURVEY 8d's heavy variant of config3, each with both arms.
     One child process per arm; device timed like the main line; a few seconds each."""
     res = {}
-    for name, wl, steps, extra in (("config2", "config2", 40, []), ("config4", "config4", 20, []),
-                                   ("config3_heavy", "config3", 20, ["--scale-mult", "3.0", "--value-only"])):
+    # (config4: tensor sizes change every iteration — the kept offsets — so torch's caching allocator keeps calling cudaMalloc for
+    # the first dozens of iterations, 10-45 ms each; 30 warm-up iterations let its pool settle in both arms)
+    for name, wl, steps, warm, extra in (("config2", "config2", 60, 5, []), ("config4", "config4", 60, 30, []),
+                                         ("config3_heavy", "config3", 20, 5, ["--scale-mult", "3.0", "--value-only"])):
         for impl in ("ours", "reference"):
-            cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--impl", impl, "--steps", str(steps), "--warmup", "5",
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--impl", impl, "--steps", str(steps), "--warmup", str(warm),
                    "--no-cpu-baseline", "--no-other-configs"] + extra
             try:
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
