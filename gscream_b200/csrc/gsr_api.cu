@@ -352,6 +352,7 @@ int gsr_decode_stage1(int A, int feat_dim, int n_offsets, const float *anchor, c
 	if (A == 0) return 0;
 	DecodeWeights wt;
 	if (!anchor || !anchor_feat || !campos || !scratch || !neural_opacity || !mask || !unpack_weights(mlp_params, wt)) return GSR_E_BADARG;
+	if (!aligned16(anchor_feat)) return GSR_E_BADARG;   // feature rows are read as float4
 	const DecodeLayout L = decode_layout(A);
 	if (scratch_bytes < L.total || !aligned16(scratch)) return GSR_E_WORKSPACE;
 	StageTimer t(kDecodeFwd, stream);
@@ -365,6 +366,7 @@ static int fill_decode_args(DecodeArgs &a, int A, int feat_dim, int n_offsets, i
 {
 	if (A <= 0 || n_vis < 0 || n_vis > A || P < 0 || P > n_vis * n_offsets || !gsr_decode_supported(feat_dim, n_offsets)) return GSR_E_BADARG;
 	if (!anchor || !anchor_feat || !offset || !scaling || !campos || !scratch || !unpack_weights(mlp_params, a.wt)) return GSR_E_BADARG;
+	if (!aligned16(anchor_feat)) return GSR_E_BADARG;   // feature rows are read as float4
 	const DecodeLayout L = decode_layout(A);
 	if (scratch_bytes < L.total || !aligned16(scratch)) return GSR_E_WORKSPACE;
 	char *s = (char *)scratch;
@@ -418,7 +420,7 @@ int gsr_decode_backward(int A, int feat_dim, int n_offsets, int64_t n_vis, int64
 	DecodeBwdArgs b{};
 	const int rc = fill_decode_args(b.f, A, feat_dim, n_offsets, n_vis, P, anchor, anchor_feat, offset, scaling, campos, mlp_params, scratch, scratch_bytes);
 	if (rc) return rc;
-	if (!g_anchor || !g_feat || !g_offset || !g_scaling || !g_mlp_params) return GSR_E_BADARG;
+	if (!g_anchor || !g_feat || !g_offset || !g_scaling || !g_mlp_params || !aligned16(g_feat)) return GSR_E_BADARG;
 	for (int m = 0; m < 4; m++) {
 		b.g_w1[m] = g_mlp_params[4 * m + 0]; b.g_b1[m] = g_mlp_params[4 * m + 1]; b.g_w2[m] = g_mlp_params[4 * m + 2]; b.g_b2[m] = g_mlp_params[4 * m + 3];
 		if (!b.g_w1[m] || !b.g_b1[m] || !b.g_w2[m] || !b.g_b2[m]) return GSR_E_BADARG;

@@ -11,10 +11,28 @@
 //   stage 2: the other three MLPs + post-processing, written straight into the compacted SoA outputs
 //   backward: one kernel that recomputes the activations, back-propagates to anchor / feature / offset / scaling
 //             and accumulates the sixteen weight / bias gradients on chip (registers across a persistent CTA).
-// Work decomposition: one warp decodes kDecNA = 4 anchors at a time; lane = hidden unit in layer 1 (the hidden
-// width, the feature width and the warp width are all 32), lane = output unit in layer 2; weights live in shared
-// memory in the layouts that make both conflict-free.  The arithmetic is plain fp32 FMA; the whole decode is
-// ~8.4 kMAC per anchor, far below the rasterizer's cost, so no tensor cores are used here.
+//
+// The MLPs run on the tensor pipe: mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo; lo*hi + hi*lo + hi*hi, FP32
+// accumulate — FP32-grade products, as in the blend kernels).  Every operand map below is modelled lane by lane in
+// tests/_decode_fragments.py (same names, same expressions) and checked against plain matrix products on the CPU
+// (tests/test_decode_fragments.py).  With lane = 4 g + t:
+//     A  a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)      B  b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//     C  c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+// "Part A" (all three kernels): one warp owns a tile of 16 visible anchors = the M dimension.  The gather builds the A
+// fragments of x straight from global memory (lane t reads feat[8t .. 8t+7] of rows g and g+8; the contraction slots are
+// permuted to match, in1()), layer 1 leaves H as C fragments, and a C fragment IS the A fragment of the next product when
+// contraction slot t is column 2t and slot t+4 is column 2t+1 (c_as_a) — so layer 2 forward (H -> OUT) and layer 1 backward
+// (dH -> dx) chain in registers.  The 12k pre-activations go to a per-warp shared-memory tile OUT[16][S] where the
+// per-(anchor, offset) activations / post-processing pass picks them up (and, in the backward, replaces them by their
+// gradients in place).  The weights sit in shared memory in fragment order (one conflict-free LDS.128 per lane brings the B
+// fragments of two tiles).
+// "Part B" (backward only): the weight gradients contract over anchors, which a C fragment of part A holds along its rows —
+// the one dimension that cannot become a contraction index without a transpose.  So after a CTA barrier warp (m, hh) —
+// MLP m, hidden units 16hh .. 16hh+15 — walks over the iteration's anchors in n-tiles of 8 with the hidden units as the M
+// dimension: it recomputes H^T = relu(W1 x^T + b1) and dH^T = W2^T dOUT^T from the X / OUT tiles part A left in shared memory
+// (+1/3 MMAs), and now both C fragments have anchors along their columns: dH^T is the A operand of dW1 += dH^T x, H^T is the B
+// operand of dW2 += dOUT^T H.  The accumulators (<= 92 registers per lane) stay in registers across the persistent CTA's
+// anchors; one atomic per entry at the end.
 #include "gsr_internal.cuh"
 #include "gsr_sort.cuh"
 #include "gsr_decode.cuh"
@@ -25,223 +43,342 @@ namespace {
 
 constexpr int kHid = 32;          // hidden width == feat_dim == warp width
 constexpr int kIn = 36;           // feat_dim + 3 + 1
-constexpr int kNA = kDecNA;       // anchors per warp iteration
+constexpr int kTile = kDecNA;     // anchors per warp tile (the M dimension of part A)
 constexpr int kWarps = 8;
-constexpr int kHStride = 33;      // H4[m][h] rows padded so that lanes of different MLPs hit different banks
+constexpr int kSX = 41;           // X tile row stride: [0..31] feat, [32..34] view dir, [35] dist, [36..39] their gradients, [40] anchor id
+constexpr int kPP = 9;            // per (anchor, offset) partials: d anchor (3), d get_scaling (6)
+constexpr unsigned kFull = 0xffffffffu;
 
-__host__ __device__ inline int out_base(int m, int k) { return m == 0 ? 0 : m == 1 ? k : m == 2 ? 2 * k : 9 * k; }
 __host__ __device__ inline int out_count(int m, int k) { return m == 0 ? k : m == 1 ? k : m == 2 ? 7 * k : 3 * k; }
-__device__ __forceinline__ int mlp_of(int o, int k) { return o < k ? 0 : (o < 2 * k ? 1 : (o < 9 * k ? 2 : 3)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// shared-memory carve-up (in floats).  One padded copy of each weight matrix serves both access patterns:
-//   W1 as [m][i][33]  : forward layer 1 reads a row with lane = h (consecutive), backward layer 1 a column with lane = i (stride 33)
-//   W2 as [h][Os], Os odd >= 12k : forward layer 2 reads with lane = o (consecutive), backward layer 2 with lane = h (stride Os)
-constexpr int kW1Stride = kHid + 1;
-struct SmemPlan {
-	int w1, b1, w2, os, b2, warp0, per_warp, x4, h4, dh4, out4, pp, total;
+// Column plan of the OUT tile for the MLPs [m0, m1): each MLP padded to a multiple of 16 columns (pad columns hold zeros),
+// row stride S = cols + 4 (S = 4 mod 8 with S/4 odd: the fragment loads of parts A and B are bank-conflict free).
+struct ColPlan {
+	int cb[4], cols, S;
 };
-__host__ __device__ inline SmemPlan smem_plan(int k, bool backward)
+__host__ __device__ inline ColPlan col_plan(int k, int m0, int m1)
 {
-	const int O = 12 * k;
-	const int Opad = (O + 3) & ~3;
-	SmemPlan p{};
-	int off = 0;
-	p.w1 = off;  off += 4 * kIn * kW1Stride;
-	p.b1 = off;  off += 4 * kHid;
-	p.os = O | 1;
-	p.w2 = off;  off += kHid * p.os;
-	p.b2 = off;  off += Opad;
-	off = (off + 3) & ~3;
-	p.warp0 = off;
-	int w = 0;
-	p.x4 = w;   w += kIn * kNA;                         // [i][a]
-	p.h4 = w;   w += 4 * kHStride * kNA;                // [m][h(+1)][a]
-	p.dh4 = w;  if (backward) w += 4 * kHStride * kNA;
-	p.out4 = w; w += Opad * kNA;                        // [o][a]  (pre-activations, then their gradients in place)
-	p.pp = w;   if (backward) w += ((kNA * k * 10 + 3) & ~3); // per (anchor, offset) partials: dxyz(3) dgs(6)
-	p.per_warp = w;
-	p.total = off + kWarps * w;
+	ColPlan p{};
+	int c = 0;
+	for (int m = 0; m < 4; m++) {
+		p.cb[m] = c;
+		if (m >= m0 && m < m1) c += (out_count(m, k) + 15) / 16 * 16;
+	}
+	p.cols = c;
+	p.S = c + 4;
 	return p;
 }
 
-struct GroupIO {
-	int id[kNA];
-	bool valid[kNA];
-	float ax[kNA], ay[kNA], az[kNA];   // anchor position
-	float ux[kNA], uy[kNA], uz[kNA];   // normalised view direction
-	float dist[kNA];
+// shared-memory carve-up (in floats)
+struct SmemPlan {
+	int w1f, w2f, w1b, w2b, b1, b2, warp0, per_warp, out, x, pp, total;
 };
-
-__device__ __forceinline__ void load_weights(float *sm, const SmemPlan &pl, const DecodeWeights &wt, int k, int tid)
+__host__ __device__ inline SmemPlan smem_plan(int k, int m0, int m1, bool backward, int tiles)
 {
-	const int O = 12 * k;
-	for (int idx = tid; idx < 4 * kHid * kIn; idx += 256) {
-		const int m = idx / (kHid * kIn), rem = idx % (kHid * kIn), h = rem / kIn, i = rem % kIn;
-		sm[pl.w1 + (m * kIn + i) * kW1Stride + h] = __ldg(wt.w1[m] + rem);
-	}
-	for (int idx = tid; idx < 4 * kHid; idx += 256) sm[pl.b1 + idx] = __ldg(wt.b1[idx >> 5] + (idx & 31));
-	for (int idx = tid; idx < O * kHid; idx += 256) {
-		const int o = idx / kHid, h = idx % kHid;
-		const int m = o < k ? 0 : (o < 2 * k ? 1 : (o < 9 * k ? 2 : 3));
-		sm[pl.w2 + h * pl.os + o] = __ldg(wt.w2[m] + (o - out_base(m, k)) * kHid + h);
-	}
-	for (int o = tid; o < O; o += 256) {
-		const int m = o < k ? 0 : (o < 2 * k ? 1 : (o < 9 * k ? 2 : 3));
-		sm[pl.b2 + o] = __ldg(wt.b2[m] + (o - out_base(m, k)));
-	}
+	const ColPlan cp = col_plan(k, m0, m1);
+	const int nm = m1 - m0;
+	SmemPlan p{};
+	int off = 0;
+	p.w1f = off;  off += nm * 5 * 2 * 32 * 4;
+	p.w2f = off;  off += (cp.cols / 8) * 2 * 32 * 4;
+	p.w1b = off;  if (backward) off += nm * 2 * 5 * 32 * 4;
+	p.w2b = off;  if (backward) off += (cp.cols / 8) * 2 * 32 * 4;
+	p.b1 = off;   off += nm * kHid;
+	p.b2 = off;   off += cp.cols + 8;
+	off = (off + 3) & ~3;
+	p.warp0 = off;
+	int w = 0;
+	p.out = w;  w += kTile * cp.S;
+	p.x = w;    if (backward) w += kTile * kSX;
+	p.pp = w;   if (backward) w += kTile * k * kPP;
+	w = (w + 3) & ~3;
+	p.per_warp = w;
+	p.total = off + tiles * w;
+	return p;
 }
 
-// One group of kNA visible anchors as it comes from global memory.  Fetched one loop iteration ahead of its use, so that the
-// two dependent loads (visible list -> anchor row / feature row) are off the critical path of the MLP arithmetic.
-struct GroupRaw {
-	int id[kNA];
-	bool valid[kNA];
-	float f[kNA];                      // feature `lane` of each anchor
-	float ax[kNA], ay[kNA], az[kNA];
+// ---- tensor-pipe helpers (the same instruction and split as gsr_blend.cuh) ---------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+	hi = __float_as_uint(x) & 0xffffe000u;
+	lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+	asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct AFrag {
+	uint32_t hi[4], lo[4];
 };
-__device__ __forceinline__ void fetch_group(GroupRaw &r, int g, int groups, int n_vis, const uint32_t *__restrict__ vis_ids,
-                                            const float *__restrict__ anchor, const float *__restrict__ feat, int lane)
+__device__ __forceinline__ AFrag make_a(float a0, float a1, float a2, float a3)
 {
-#pragma unroll
-	for (int a = 0; a < kNA; a++) {
-		const int rank = g * kNA + a;
-		r.valid[a] = g < groups && rank < n_vis;
-		r.id[a] = r.valid[a] ? (vis_ids ? (int)__ldg(vis_ids + rank) : rank) : 0;
-	}
-#pragma unroll
-	for (int a = 0; a < kNA; a++) {
-		r.f[a] = r.ax[a] = r.ay[a] = r.az[a] = 0.f;
-		if (r.valid[a]) {
-			r.f[a] = __ldg(feat + (size_t)r.id[a] * kHid + lane);
-			r.ax[a] = __ldg(anchor + (size_t)r.id[a] * 3 + 0);
-			r.ay[a] = __ldg(anchor + (size_t)r.id[a] * 3 + 1);
-			r.az[a] = __ldg(anchor + (size_t)r.id[a] * 3 + 2);
-		}
-	}
+	AFrag f;
+	split_tf32(a0, f.hi[0], f.lo[0]);
+	split_tf32(a1, f.hi[1], f.lo[1]);
+	split_tf32(a2, f.hi[2], f.lo[2]);
+	split_tf32(a3, f.hi[3], f.lo[3]);
+	return f;
 }
-// Build X4[i][a] = [feat | ob_view | ob_dist] (gaussian_renderer/__init__.py:26-52).  Anchors past n_vis contribute zeros.
-__device__ __forceinline__ void stage_group(GroupIO &io, float *X4, const GroupRaw &r, float cx, float cy, float cz, int lane)
+// a C fragment as the A fragment of the next product: contraction slot t <-> column 2t, slot t+4 <-> column 2t+1
+__device__ __forceinline__ AFrag c_as_a(const float (&c)[4]) { return make_a(c[0], c[2], c[1], c[3]); }
+// c += a b with FP32-grade products
+__device__ __forceinline__ void mma3(float (&c)[4], const AFrag &a, float b0, float b1)
 {
-#pragma unroll
-	for (int a = 0; a < kNA; a++) {
-		io.valid[a] = r.valid[a];
-		io.id[a] = r.id[a];
-		io.ax[a] = r.ax[a]; io.ay[a] = r.ay[a]; io.az[a] = r.az[a];
-		io.ux[a] = io.uy[a] = io.uz[a] = 0.f;
-		io.dist[a] = 0.f;
-		if (io.valid[a]) {
-			const float vx = io.ax[a] - cx, vy = io.ay[a] - cy, vz = io.az[a] - cz;
-			io.dist[a] = sqrtf(vx * vx + vy * vy + vz * vz);
-			io.ux[a] = vx / io.dist[a];
-			io.uy[a] = vy / io.dist[a];
-			io.uz[a] = vz / io.dist[a];
+	uint32_t b0h, b0l, b1h, b1l;
+	split_tf32(b0, b0h, b0l);
+	split_tf32(b1, b1h, b1l);
+	mma_tf32(c, a.lo, b0h, b1h);
+	mma_tf32(c, a.hi, b0l, b1l);
+	mma_tf32(c, a.hi, b0h, b1h);
+}
+__device__ __forceinline__ float f4c(const float4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// ---- input-slot maps ---------------------------------------------------------------------------------------------------------
+// layer-1 contraction slot s (0..7) of k-step ks (0..4) -> input index, -1 = zero pad.  Lane t holds feat[8t .. 8t+7] as two
+// float4 F0, F1: slot t of k-step ks is F0[ks], slot t+4 is F1[ks]; k-step 4 carries (ux, uy, uz, dist) in slots 0..3.
+__host__ __device__ inline int in1(int ks, int s) { return ks < 4 ? 8 * (s & 3) + 4 * (s >> 2) + ks : (s < 4 ? 32 + s : -1); }
+// layer-1 backward output column c (0..7) of n-tile nt (0..4) -> input index: lane t ends up with d feat[8t .. 8t+7] in tiles
+// 0..3 (two float4 stores); tile 4 carries the view / distance gradients in columns 0..3.
+__host__ __device__ inline int in1b(int nt, int c) { return nt < 4 ? 8 * (c >> 1) + 2 * nt + (c & 1) : (c < 4 ? 32 + c : -1); }
+
+// ---- shared-memory weight copies in fragment order ---------------------------------------------------------------------------
+//   W1F[m][ks][p][lane][4]   (b0, b1) of n-tiles 2p, 2p+1:    b0 = W1[m][8nt+g][in1(ks,t)]      b1 = W1[m][8nt+g][in1(ks,t+4)]
+//   W2F[tile8][ksp][lane][4] (b0, b1) of k-steps 2ksp, +1:    b0 = W2[m][8nt+g][8ks+2t]         b1 = W2[m][8nt+g][8ks+2t+1]
+//   W1B[m][ksp][nt][lane][4] (b0, b1) of k-steps 2ksp, +1:    b0 = W1[m][8ks+2t][in1b(nt,g)]    b1 = W1[m][8ks+2t+1][in1b(nt,g)]
+//   W2B[tile8][p][lane][4]   (b0, b1) of n-tiles 2p, 2p+1:    b0 = W2[m][8ks+t][8nt+g]          b1 = W2[m][8ks+t+4][8nt+g]
+// (tile8 = (cb[m] / 8) + tile index inside MLP m; rows o >= out_count(m) are zeros).  W1F and W2B double as the A operands of
+// part B: read as (a0, a2, a1, a3) of the 16 hidden units 16p .. 16p+15.
+__device__ __forceinline__ void load_weights(float *sm, const SmemPlan &pl, const ColPlan &cp, const DecodeWeights &wt, int k, int m0, int m1,
+                                             bool backward, int tid)
+{
+	const int nm = m1 - m0;
+	for (int idx = tid; idx < nm * 1280; idx += 256) {
+		const int e = idx & 3, lane = (idx >> 2) & 31, g = lane >> 2, t = lane & 3;
+		{   // W1F
+			const int p = (idx >> 7) & 1, ks = (idx >> 8) % 5, m = m0 + idx / 1280;
+			const int nt = 2 * p + (e >> 1), i = in1(ks, t + 4 * (e & 1));
+			sm[pl.w1f + idx] = i < 0 ? 0.f : __ldg(wt.w1[m] + (8 * nt + g) * kIn + i);
 		}
-		X4[lane * kNA + a] = r.f[a];
-		if (lane < 4) X4[(kHid + lane) * kNA + a] = lane == 0 ? io.ux[a] : lane == 1 ? io.uy[a] : lane == 2 ? io.uz[a] : io.dist[a];
+		if (backward) {   // W1B
+			const int nt = (idx >> 7) % 5, ksp = ((idx >> 7) / 5) & 1, m = m0 + idx / 1280;
+			const int h = 8 * (2 * ksp + (e >> 1)) + 2 * t + (e & 1), i = in1b(nt, g);
+			sm[pl.w1b + idx] = i < 0 ? 0.f : __ldg(wt.w1[m] + h * kIn + i);
+		}
 	}
-	__syncwarp();
+	for (int idx = tid; idx < cp.cols * 32; idx += 256) {
+		const int e = idx & 3, lane = (idx >> 2) & 31, g = lane >> 2, t = lane & 3;
+		const int q = (idx >> 7) & 1, tile8 = idx >> 8;
+		int m = m0;
+		while (m + 1 < m1 && cp.cb[m + 1] <= 8 * tile8) m++;
+		const int tl = tile8 - cp.cb[m] / 8, n_m = out_count(m, k);
+		{   // W2F: q = ksp
+			const int o = 8 * tl + g, h = 8 * (2 * q + (e >> 1)) + 2 * t + (e & 1);
+			sm[pl.w2f + idx] = o < n_m ? __ldg(wt.w2[m] + o * kHid + h) : 0.f;
+		}
+		if (backward) {   // W2B: q = p
+			const int o = 8 * tl + t + 4 * (e & 1), h = 8 * (2 * q + (e >> 1)) + g;
+			sm[pl.w2b + idx] = o < n_m ? __ldg(wt.w2[m] + o * kHid + h) : 0.f;
+		}
+	}
+	for (int idx = tid; idx < nm * kHid; idx += 256) sm[pl.b1 + idx] = __ldg(wt.b1[m0 + (idx >> 5)] + (idx & 31));
+	for (int c = tid; c < cp.cols + 8; c += 256) {
+		float v = 0.f;
+		for (int m = m0; m < m1; m++)
+			if (c >= cp.cb[m] && c < cp.cb[m] + out_count(m, k)) v = __ldg(wt.b2[m] + (c - cp.cb[m]));
+		sm[pl.b2 + c] = v;
+	}
 }
 
-// Layer 1 of MLPs m0..m1-1: lane = hidden unit.  H4[m][lane][a] = relu(b1 + sum_i W1[lane][i] x[i][a]).
-template <int M0, int M1>
-__device__ __forceinline__ void layer1(const float *sm, const SmemPlan &pl, const float *X4, float *H4, int lane)
+// ---- the gather ---------------------------------------------------------------------------------------------------------------
+// One tile of 16 visible anchors as it comes from global memory: lane (g, t) holds rows g and g+8.  Fetched one loop iteration
+// ahead of its use, so that the two dependent loads (visible list -> anchor row / feature row) are off the critical path.
+struct TileRaw {
+	int id[2];
+	bool valid[2];
+	float4 f[2][2];                 // feat[8t .. 8t+3], feat[8t+4 .. 8t+7]
+	float ax[2], ay[2], az[2];
+};
+__device__ __forceinline__ void fetch_tile(TileRaw &r, int tile, int ntiles, int n_vis, const uint32_t *__restrict__ vis_ids,
+                                           const float *__restrict__ anchor, const float *__restrict__ feat, int g, int t)
 {
-	float acc[M1 - M0][kNA];
 #pragma unroll
-	for (int m = M0; m < M1; m++) {
-		const float b = sm[pl.b1 + m * kHid + lane];
-#pragma unroll
-		for (int a = 0; a < kNA; a++) acc[m - M0][a] = b;
+	for (int q = 0; q < 2; q++) {
+		const int rank = tile * kTile + g + 8 * q;
+		r.valid[q] = tile < ntiles && rank < n_vis;
+		r.id[q] = r.valid[q] ? (vis_ids ? (int)__ldg(vis_ids + rank) : rank) : 0;
 	}
-#pragma unroll 4
-	for (int i = 0; i < kIn; i++) {
-		const float4 x = *reinterpret_cast<const float4 *>(X4 + i * kNA);
 #pragma unroll
-		for (int m = M0; m < M1; m++) {
-			const float w = sm[pl.w1 + (m * kIn + i) * kW1Stride + lane];
-			acc[m - M0][0] = fmaf(w, x.x, acc[m - M0][0]);
-			acc[m - M0][1] = fmaf(w, x.y, acc[m - M0][1]);
-			acc[m - M0][2] = fmaf(w, x.z, acc[m - M0][2]);
-			acc[m - M0][3] = fmaf(w, x.w, acc[m - M0][3]);
+	for (int q = 0; q < 2; q++) {
+		r.f[q][0] = r.f[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+		r.ax[q] = r.ay[q] = r.az[q] = 0.f;
+		if (r.valid[q]) {
+			const float4 *row = reinterpret_cast<const float4 *>(feat + (size_t)r.id[q] * kHid + 8 * t);
+			r.f[q][0] = __ldg(row);
+			r.f[q][1] = __ldg(row + 1);
+			r.ax[q] = __ldg(anchor + (size_t)r.id[q] * 3 + 0);
+			r.ay[q] = __ldg(anchor + (size_t)r.id[q] * 3 + 1);
+			r.az[q] = __ldg(anchor + (size_t)r.id[q] * 3 + 2);
+		}
+	}
+}
+// The tile's input x = [feat | ob_view | ob_dist] (gaussian_renderer/__init__.py:26-52) as A-fragment values: xa[ks] =
+// (row g slot t, row g+8 slot t, row g slot t+4, row g+8 slot t+4).  Rows past n_vis are zeros.
+struct TileX {
+	float xa[5][4];
+	float u[2][3], dist[2];
+};
+__device__ __forceinline__ void stage_tile(TileX &x, const TileRaw &r, float cx, float cy, float cz, int t)
+{
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		x.u[q][0] = x.u[q][1] = x.u[q][2] = 0.f;
+		x.dist[q] = 0.f;
+		if (r.valid[q]) {
+			const float vx = r.ax[q] - cx, vy = r.ay[q] - cy, vz = r.az[q] - cz;
+			x.dist[q] = sqrtf(vx * vx + vy * vy + vz * vz);
+			x.u[q][0] = vx / x.dist[q];
+			x.u[q][1] = vy / x.dist[q];
+			x.u[q][2] = vz / x.dist[q];
 		}
 	}
 #pragma unroll
-	for (int m = M0; m < M1; m++) {
-		float4 h = {fmaxf(acc[m - M0][0], 0.f), fmaxf(acc[m - M0][1], 0.f), fmaxf(acc[m - M0][2], 0.f), fmaxf(acc[m - M0][3], 0.f)};
-		*reinterpret_cast<float4 *>(H4 + (m * kHStride + lane) * kNA) = h;
+	for (int ks = 0; ks < 4; ks++) {
+		x.xa[ks][0] = f4c(r.f[0][0], ks);
+		x.xa[ks][1] = f4c(r.f[1][0], ks);
+		x.xa[ks][2] = f4c(r.f[0][1], ks);
+		x.xa[ks][3] = f4c(r.f[1][1], ks);
 	}
-	__syncwarp();
+#pragma unroll
+	for (int q = 0; q < 2; q++) x.xa[4][q] = t == 0 ? x.u[q][0] : t == 1 ? x.u[q][1] : t == 2 ? x.u[q][2] : x.dist[q];
+	x.xa[4][2] = x.xa[4][3] = 0.f;
 }
 
-// Layer 2 for outputs [o_begin, o_end): lane = output unit.  OUT4[o][a] = b2[o] + sum_h W2[o][h] H[m(o)][h][a].
-__device__ __forceinline__ void layer2(const float *sm, const SmemPlan &pl, const float *H4, float *OUT4, int k, int o_begin, int o_end, int lane)
+// ---- part A products ----------------------------------------------------------------------------------------------------------
+// layer 1 of MLP m (ml = m - m0): h[nt] = C fragments of relu(x W1^T + b1): rows = anchors, columns = hidden units 8nt + 2t, +1
+__device__ __forceinline__ void layer1_forward(float (&h)[4][4], const TileX &x, const float *sm, const SmemPlan &pl, int ml, int lane, int t)
 {
-	for (int o0 = o_begin; o0 < o_end; o0 += 32) {
-		const int o = o0 + lane;
-		const bool on = o < o_end;
-		const int oc = on ? o : o_begin;
-		const int m = mlp_of(oc, k);
-		const float b = sm[pl.b2 + oc];
-		float acc0 = b, acc1 = b, acc2 = b, acc3 = b;
-		const float *hrow = H4 + m * kHStride * kNA;
-#pragma unroll 8
-		for (int h = 0; h < kHid; h++) {
-			const float w = sm[pl.w2 + h * pl.os + oc];
-			const float4 hv = *reinterpret_cast<const float4 *>(hrow + h * kNA);
-			acc0 = fmaf(w, hv.x, acc0);
-			acc1 = fmaf(w, hv.y, acc1);
-			acc2 = fmaf(w, hv.z, acc2);
-			acc3 = fmaf(w, hv.w, acc3);
-		}
-		if (on) *reinterpret_cast<float4 *>(OUT4 + o * kNA) = make_float4(acc0, acc1, acc2, acc3);
+#pragma unroll
+	for (int nt = 0; nt < 4; nt++) {
+		const float2 b = *reinterpret_cast<const float2 *>(sm + pl.b1 + ml * kHid + 8 * nt + 2 * t);
+		h[nt][0] = h[nt][2] = b.x;
+		h[nt][1] = h[nt][3] = b.y;
 	}
-	__syncwarp();
+#pragma unroll
+	for (int ks = 0; ks < 5; ks++) {
+		const AFrag a = make_a(x.xa[ks][0], x.xa[ks][1], x.xa[ks][2], x.xa[ks][3]);
+#pragma unroll
+		for (int p = 0; p < 2; p++) {
+			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w1f + (((ml * 5 + ks) * 2 + p) * 32 + lane) * 4);
+			mma3(h[2 * p], a, e.x, e.y);
+			mma3(h[2 * p + 1], a, e.z, e.w);
+		}
+	}
+#pragma unroll
+	for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+		for (int e = 0; e < 4; e++) h[nt][e] = fmaxf(h[nt][e], 0.f);
+}
+// layer 2 of MLP m: OUT[a][cb + o] = b2[o] + sum_h W2[o][h] H[a][h], H from the C fragments of layer 1
+__device__ __forceinline__ void layer2_forward(const float (&h)[4][4], const float *sm, const SmemPlan &pl, float *OUT, int S, int cb, int n_m,
+                                               int lane, int g, int t)
+{
+	AFrag ha[4];
+#pragma unroll
+	for (int ks = 0; ks < 4; ks++) ha[ks] = c_as_a(h[ks]);
+	const int nt8 = (n_m + 7) >> 3;
+	for (int nt = 0; nt < nt8; nt++) {
+		const int col = cb + 8 * nt + 2 * t;
+		const float2 b = *reinterpret_cast<const float2 *>(sm + pl.b2 + col);
+		float acc[4] = {b.x, b.y, b.x, b.y};
+#pragma unroll
+		for (int ksp = 0; ksp < 2; ksp++) {
+			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w2f + (((cb >> 3) + nt) * 2 + ksp) * 128 + lane * 4);
+			mma3(acc, ha[2 * ksp], e.x, e.y);
+			mma3(acc, ha[2 * ksp + 1], e.z, e.w);
+		}
+		*reinterpret_cast<float2 *>(OUT + g * S + col) = make_float2(acc[0], acc[1]);
+		*reinterpret_cast<float2 *>(OUT + (g + 8) * S + col) = make_float2(acc[2], acc[3]);
+	}
+}
+// layer 2 backward of MLP m: dh[nt] = C fragments of dOUT[:, MLP m] W2 (rows = anchors, columns = hidden 8nt + 2t, +1), not gated
+__device__ __forceinline__ void layer2_backward(float (&dh)[4][4], const float *sm, const SmemPlan &pl, const float *OUT, int S, int cb, int n_m,
+                                                int lane, int g, int t)
+{
+#pragma unroll
+	for (int nt = 0; nt < 4; nt++) dh[nt][0] = dh[nt][1] = dh[nt][2] = dh[nt][3] = 0.f;
+	const int nks = (n_m + 7) >> 3;
+	for (int ks = 0; ks < nks; ks++) {
+		const float *r0 = OUT + g * S + cb + 8 * ks + t, *r1 = r0 + 8 * S;
+		const AFrag a = make_a(r0[0], r1[0], r0[4], r1[4]);
+#pragma unroll
+		for (int p = 0; p < 2; p++) {
+			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w2b + (((cb >> 3) + ks) * 2 + p) * 128 + lane * 4);
+			mma3(dh[2 * p], a, e.x, e.y);
+			mma3(dh[2 * p + 1], a, e.z, e.w);
+		}
+	}
+}
+// layer 1 backward of MLP m: dx[nt] += dh W1; afterwards lane t holds d feat[8t + 2nt + e] of rows g (c0, c1) and g+8 (c2, c3)
+__device__ __forceinline__ void layer1_backward(float (&dx)[5][4], const float (&dh)[4][4], const float *sm, const SmemPlan &pl, int ml, int lane)
+{
+#pragma unroll
+	for (int ksp = 0; ksp < 2; ksp++) {
+		const AFrag a0 = c_as_a(dh[2 * ksp]), a1 = c_as_a(dh[2 * ksp + 1]);
+#pragma unroll
+		for (int nt = 0; nt < 5; nt++) {
+			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w1b + (((ml * 2 + ksp) * 5 + nt) * 32 + lane) * 4);
+			mma3(dx[nt], a0, e.x, e.y);
+			mma3(dx[nt], a1, e.z, e.w);
+		}
+	}
 }
 
 // ---- stage 1: opacity MLP, mask, per-anchor counts ---------------------------------------------------------------
-__global__ void __launch_bounds__(256) decode_opacity_kernel(DecodeArgs a)
+__global__ void __launch_bounds__(256, 2) decode_opacity_kernel(DecodeArgs a)
 {
 	extern __shared__ __align__(16) float sm[];
 	const int k = a.k;
-	const SmemPlan pl = smem_plan(k, false);
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	load_weights(sm, pl, a.wt, k, tid);
+	const ColPlan cp = col_plan(k, 0, 1);
+	const SmemPlan pl = smem_plan(k, 0, 1, false, kWarps);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+	for (int i = tid; i < kWarps * pl.per_warp; i += 256) sm[pl.warp0 + i] = 0.f;
+	load_weights(sm, pl, cp, a.wt, k, 0, 1, false, tid);
 	__syncthreads();
-	float *X4 = sm + pl.warp0 + warp * pl.per_warp + pl.x4;
-	float *H4 = sm + pl.warp0 + warp * pl.per_warp + pl.h4;
-	float *OUT4 = sm + pl.warp0 + warp * pl.per_warp + pl.out4;
+	float *OUT = sm + pl.warp0 + warp * pl.per_warp + pl.out;
+	const int S = cp.S;
 	const int n_vis = a.n_vis_dev ? (int)*a.n_vis_dev : a.n_vis;
-	const int groups = (n_vis + kNA - 1) / kNA;
+	const int ntiles = (n_vis + kTile - 1) / kTile;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
-	GroupRaw raw;
-	fetch_group(raw, blockIdx.x * kWarps + warp, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
-	for (int g = blockIdx.x * kWarps + warp; g < groups; g += gridDim.x * kWarps) {
-		GroupIO io;
-		stage_group(io, X4, raw, cx, cy, cz, lane);
-		fetch_group(raw, g + gridDim.x * kWarps, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
-		layer1<0, 1>(sm, pl, X4, H4, lane);
-		layer2(sm, pl, H4, OUT4, k, 0, k, lane);
-		// lanes = (anchor, offset) pairs; k <= 16 so 4 anchors need at most two rounds
-		for (int idx = lane; idx < kNA * k; idx += 32) {
-			const int aa = idx / k, j = idx % k;
-			const int r = g * kNA + aa;
-			const bool valid = r < n_vis;
-			const float nop = tanhf(OUT4[j * kNA + aa]);
-			const bool keep = valid && nop > 0.0f;                       // gaussian_renderer/__init__.py:59
-			if (valid) {
+	TileRaw raw;
+	fetch_tile(raw, blockIdx.x * kWarps + warp, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+	for (int tile = blockIdx.x * kWarps + warp; tile < ntiles; tile += gridDim.x * kWarps) {
+		TileX x;
+		stage_tile(x, raw, cx, cy, cz, t);
+		fetch_tile(raw, tile + gridDim.x * kWarps, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+		float h[4][4];
+		layer1_forward(h, x, sm, pl, 0, lane, t);
+		layer2_forward(h, sm, pl, OUT, S, 0, k, lane, g, t);
+		__syncwarp();
+		// lanes = (anchor, offset) pairs
+		for (int idx = lane; idx < kTile * k; idx += 32) {
+			const int aa = idx / k, j = idx - aa * k;
+			const int r = tile * kTile + aa;
+			if (r < n_vis) {
+				const float nop = tanhf(OUT[aa * S + j]);
 				a.neural_opacity[(size_t)r * k + j] = nop;
-				a.mask[(size_t)r * k + j] = keep ? 1 : 0;
+				a.mask[(size_t)r * k + j] = nop > 0.0f ? 1 : 0;                  // gaussian_renderer/__init__.py:59
 			}
 		}
-		__syncwarp();
-		// per-anchor count and bit mask: lanes 0..3 re-read their anchor's k pre-activations (cheap, shared memory)
-		if (lane < kNA) {
-			const int r = g * kNA + lane;
+		// per-anchor count and bit mask: lanes 0..15 re-read their anchor's k pre-activations (cheap, shared memory)
+		if (lane < kTile) {
+			const int r = tile * kTile + lane;
 			if (r < n_vis) {
 				uint32_t bits = 0;
 				for (int j = 0; j < k; j++)
-					if (tanhf(OUT4[j * kNA + lane]) > 0.0f) bits |= 1u << j;
+					if (tanhf(OUT[lane * S + j]) > 0.0f) bits |= 1u << j;
 				a.count[r] = (uint32_t)__popc(bits);
 				a.maskbits[r] = bits;
 			}
@@ -251,31 +388,37 @@ __global__ void __launch_bounds__(256) decode_opacity_kernel(DecodeArgs a)
 }
 
 // ---- stage 2: the other three MLPs + post-processing into the compacted outputs ------------------------------------
-__global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a)
+__global__ void __launch_bounds__(256, 2) decode_outputs_kernel(DecodeArgs a)
 {
 	extern __shared__ __align__(16) float sm[];
 	const int k = a.k;
-	const SmemPlan pl = smem_plan(k, false);
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	load_weights(sm, pl, a.wt, k, tid);
+	const ColPlan cp = col_plan(k, 1, 4);
+	const SmemPlan pl = smem_plan(k, 1, 4, false, kWarps);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+	for (int i = tid; i < kWarps * pl.per_warp; i += 256) sm[pl.warp0 + i] = 0.f;
+	load_weights(sm, pl, cp, a.wt, k, 1, 4, false, tid);
 	__syncthreads();
-	float *X4 = sm + pl.warp0 + warp * pl.per_warp + pl.x4;
-	float *H4 = sm + pl.warp0 + warp * pl.per_warp + pl.h4;
-	float *OUT4 = sm + pl.warp0 + warp * pl.per_warp + pl.out4;
+	float *OUT = sm + pl.warp0 + warp * pl.per_warp + pl.out;
+	const int S = cp.S, cU = cp.cb[1], cC = cp.cb[2], cR = cp.cb[3];
 	const int n_vis = a.n_vis_dev ? (int)*a.n_vis_dev : a.n_vis; // (device copy when the host has not read the counts yet)
-	const int groups = (n_vis + kNA - 1) / kNA;
+	const int ntiles = (n_vis + kTile - 1) / kTile;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
-	GroupRaw raw;
-	fetch_group(raw, blockIdx.x * kWarps + warp, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
-	for (int g = blockIdx.x * kWarps + warp; g < groups; g += gridDim.x * kWarps) {
-		GroupIO io;
-		stage_group(io, X4, raw, cx, cy, cz, lane);
-		fetch_group(raw, g + gridDim.x * kWarps, groups, n_vis, a.vis_ids, a.anchor, a.feat, lane);
-		layer1<1, 4>(sm, pl, X4, H4, lane);
-		layer2(sm, pl, H4, OUT4, k, k, 12 * k, lane);
-		for (int idx = lane; idx < kNA * k; idx += 32) {
-			const int aa = idx / k, j = idx % k;
-			const int r = g * kNA + aa;
+	TileRaw raw;
+	fetch_tile(raw, blockIdx.x * kWarps + warp, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+	for (int tile = blockIdx.x * kWarps + warp; tile < ntiles; tile += gridDim.x * kWarps) {
+		TileX x;
+		stage_tile(x, raw, cx, cy, cz, t);
+		fetch_tile(raw, tile + gridDim.x * kWarps, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+#pragma unroll
+		for (int m = 1; m < 4; m++) {
+			float h[4][4];
+			layer1_forward(h, x, sm, pl, m - 1, lane, t);
+			layer2_forward(h, sm, pl, OUT, S, cp.cb[m], out_count(m, k), lane, g, t);
+		}
+		__syncwarp();
+		for (int idx = lane; idx < kTile * k; idx += 32) {
+			const int aa = idx / k, j = idx - aa * k;
+			const int r = tile * kTile + aa;
 			if (r >= n_vis) continue;
 			const uint32_t bits = __ldg(a.maskbits + r);
 			if (!((bits >> j) & 1u)) continue;
@@ -284,14 +427,15 @@ __global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a)
 			const float *gs = a.scaling + (size_t)id * 6;
 			const float *off = a.offset + ((size_t)id * k + j) * 3;
 			const float *an = a.anchor + (size_t)id * 3;
+			const float *row = OUT + aa * S;
 			a.out_opacity[p] = __ldg(a.neural_opacity + (size_t)r * k + j);
-			a.out_uncertainty[p] = sigmoidf_(OUT4[(k + j) * kNA + aa]);
+			a.out_uncertainty[p] = sigmoidf_(row[cU + j]);
 			float sr[7];
 #pragma unroll
-			for (int c = 0; c < 7; c++) sr[c] = OUT4[(2 * k + 7 * j + c) * kNA + aa];
+			for (int c = 0; c < 7; c++) sr[c] = row[cC + 7 * j + c];
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
-				a.out_color[p * 3 + c] = sigmoidf_(OUT4[(9 * k + 3 * j + c) * kNA + aa]);
+				a.out_color[p * 3 + c] = sigmoidf_(row[cR + 3 * j + c]);
 				a.out_scaling[p * 3 + c] = __ldg(gs + 3 + c) * sigmoidf_(sr[c]);                 // :89
 				a.out_xyz[p * 3 + c] = __ldg(an + c) + __ldg(off + c) * __ldg(gs + c);          // :93-94
 			}
@@ -305,234 +449,322 @@ __global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a)
 }
 
 // ---- backward -------------------------------------------------------------------------------------------------------
-// Per (warp, group of 4 anchors): recompute activations, turn the upstream gradients of the kept Gaussians into
-// gradients of the 12k output pre-activations (DOUT4, in place over OUT4), back-propagate through layer 2 (lane = h) and
-// layer 1 (lane = input i), write d_feat / d_anchor / d_offset / d_scaling.  Per CTA iteration (8 groups = 32 anchors):
-// every thread adds its slice of the weight-gradient outer products into registers; one atomic per entry at the end.
-constexpr int kAcc2 = (7 * kDecMaxK + 3) / 4;   // output rows of W2 owned by one thread (cov MLP over 4 warps)
-
-__global__ void __launch_bounds__(256, 2) decode_backward_kernel(DecodeBwdArgs a)
+// Per CTA iteration `tiles` warps run part A on one tile each: recompute the activations, turn the upstream gradients of the
+// kept Gaussians into gradients of the 12k output pre-activations (in place over OUT), back-propagate through layer 2 and
+// layer 1 in registers, write d_feat / d_anchor / d_offset / d_scaling.  After a CTA barrier all eight warps run part B over
+// the iteration's X / OUT tiles (see the file header).  KMT = 16-row tiles of the widest MLP (cov: 7k rows).
+template <int KMT>
+__global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a, int tiles)
 {
 	extern __shared__ __align__(16) float sm[];
-	const int k = a.f.k, O = 12 * k;
-	const SmemPlan pl = smem_plan(k, true);
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	load_weights(sm, pl, a.f.wt, k, tid);
+	const int k = a.f.k;
+	const ColPlan cp = col_plan(k, 0, 4);
+	const SmemPlan pl = smem_plan(k, 0, 4, true, tiles);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+	for (int i = tid; i < tiles * pl.per_warp; i += 256) sm[pl.warp0 + i] = 0.f;
+	load_weights(sm, pl, cp, a.f.wt, k, 0, 4, true, tid);
 	__syncthreads();
-	float *X4 = sm + pl.warp0 + warp * pl.per_warp + pl.x4;
-	float *H4 = sm + pl.warp0 + warp * pl.per_warp + pl.h4;
-	float *DH4 = sm + pl.warp0 + warp * pl.per_warp + pl.dh4;
-	float *OUT4 = sm + pl.warp0 + warp * pl.per_warp + pl.out4;
-	float *PP = sm + pl.warp0 + warp * pl.per_warp + pl.pp;
+	const int S = cp.S, cU = cp.cb[1], cC = cp.cb[2], cR = cp.cb[3];
+	const int my = warp < tiles ? warp : 0;
+	float *OUT = sm + pl.warp0 + my * pl.per_warp + pl.out;
+	float *X = sm + pl.warp0 + my * pl.per_warp + pl.x;
+	float *PP = sm + pl.warp0 + my * pl.per_warp + pl.pp;
 	const int n_vis = a.f.n_vis;
-	const int groups = (n_vis + kNA - 1) / kNA;
-	const int cta_iters = (groups + gridDim.x * kWarps - 1) / (gridDim.x * kWarps);
+	const int ntiles = (n_vis + kTile - 1) / kTile;
+	const int cta_iters = (ntiles + gridDim.x * tiles - 1) / (gridDim.x * tiles);
 	const float cx = __ldg(a.f.campos), cy = __ldg(a.f.campos + 1), cz = __ldg(a.f.campos + 2);
 
-	// this thread's slice of the weight gradients
-	//   W1: (m1, h = lane) x inputs [18 * half, 18 * half + 18)
-	const int m1 = (tid >> 5) & 3, half = tid >> 7;
-	float acc1[18];
+	// part B: this warp's slice of the weight gradients — MLP mB, hidden units 16hh .. 16hh+15
+	const int mB = warp >> 1, hh = warp & 1;
+	const int nB = out_count(mB, k), cbB = cp.cb[mB], nksB = (nB + 7) >> 3, nmtB = (nB + 15) >> 4;
+	float acc1[5][4], accb1[2] = {0.f, 0.f};      // dW1: rows h = 16hh + g (+8), columns i = 8nt + 2t (+1)
+	float acc2[KMT][2][4], accb2[KMT][2];         // dW2: rows o = 16mt + g (+8), columns h = 16hh + 8nt + 2t (+1)
 #pragma unroll
-	for (int q = 0; q < 18; q++) acc1[q] = 0.f;
-	float accb1 = 0.f;
-	//   W2: warps 0 / 1 own the opacity / uncertainty rows, warps 2-5 a quarter of the cov rows, warps 6-7 half of the colour rows
-	const int m2 = warp == 0 ? 0 : warp == 1 ? 1 : warp < 6 ? 2 : 3;
-	const int parts = m2 == 2 ? 4 : m2 == 3 ? 2 : 1, part = m2 == 2 ? warp - 2 : m2 == 3 ? warp - 6 : 0;
-	const int rows_m = out_count(m2, k), rows_per = (rows_m + parts - 1) / parts;
-	const int o_first = out_base(m2, k) + part * rows_per;
-	const int o_cnt = max(0, min(rows_per, rows_m - part * rows_per));
-	float acc2[kAcc2];
+	for (int nt = 0; nt < 5; nt++) acc1[nt][0] = acc1[nt][1] = acc1[nt][2] = acc1[nt][3] = 0.f;
 #pragma unroll
-	for (int q = 0; q < kAcc2; q++) acc2[q] = 0.f;
-	float accb2 = 0.f;
+	for (int mt = 0; mt < KMT; mt++) {
+		accb2[mt][0] = accb2[mt][1] = 0.f;
+#pragma unroll
+		for (int nt = 0; nt < 2; nt++) acc2[mt][nt][0] = acc2[mt][nt][1] = acc2[mt][nt][2] = acc2[mt][nt][3] = 0.f;
+	}
+	const float b1lo = sm[pl.b1 + mB * kHid + 16 * hh + g], b1hi = sm[pl.b1 + mB * kHid + 16 * hh + g + 8];
 
-	GroupRaw raw;
-	fetch_group(raw, blockIdx.x * kWarps + warp, groups, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, lane);
+	TileRaw raw;
+	fetch_tile(raw, warp < tiles ? blockIdx.x * tiles + warp : ntiles, ntiles, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, g, t);
 	for (int it = 0; it < cta_iters; it++) {
-		const int g = (it * gridDim.x + blockIdx.x) * kWarps + warp;
-		GroupIO io;
-		stage_group(io, X4, raw, cx, cy, cz, lane); // g >= groups: all invalid
-		fetch_group(raw, g + gridDim.x * kWarps, groups, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, lane);
-		layer1<0, 4>(sm, pl, X4, H4, lane);
-		layer2(sm, pl, H4, OUT4, k, 0, O, lane);
-
-		// ---- output activations backward; lanes = (anchor, offset) pairs --------------------------------------------
-		for (int idx0 = 0; idx0 < kNA * k; idx0 += 32) {
-			const int idx = idx0 + lane;
-			const bool on = idx < kNA * k;
-			const int aa = on ? idx / k : 0, j = on ? idx % k : 0;
-			const int r = g * kNA + aa;
-			const bool valid = on && g < groups && r < n_vis;
-			float d_op = 0.f, d_unc = 0.f, d_col[3] = {0.f, 0.f, 0.f}, d_sr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-			float pp[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-			if (valid) {
-				const uint32_t bits = __ldg(a.f.maskbits + r);
-				const bool keep = (bits >> j) & 1u;
-				const int aid = a.f.vis_ids ? (int)__ldg(a.f.vis_ids + r) : r;
-				const float nop = tanhf(OUT4[j * kNA + aa]);
-				float g_op = a.d_neural_opacity ? __ldg(a.d_neural_opacity + (size_t)r * k + j) : 0.f;
-				float dxyz[3] = {0.f, 0.f, 0.f};
-				if (keep) {
-					const size_t p = (size_t)(__ldg(a.f.gauss_incl + r) - (uint32_t)__popc(bits)) + __popc(bits & ((1u << j) - 1u));
-					const float *gs = a.f.scaling + (size_t)aid * 6;
-					const float *off = a.f.offset + ((size_t)aid * k + j) * 3;
-					if (a.d_opacity) g_op += __ldg(a.d_opacity + p);
-					if (a.d_uncertainty) {
-						const float s = sigmoidf_(OUT4[(k + j) * kNA + aa]);
-						d_unc = __ldg(a.d_uncertainty + p) * s * (1.f - s);
-					}
-					float sr[7];
+		const int first = (it * gridDim.x + blockIdx.x) * tiles;     // this iteration's tiles: first .. first + tiles - 1
+		const int tile = first + warp;
+		if (warp < tiles && tile < ntiles) {
+			// ================================================ part A ================================================
+			TileX x;
+			stage_tile(x, raw, cx, cy, cz, t);
+			const int id0 = raw.id[0], id1 = raw.id[1];
+			const bool v0 = raw.valid[0], v1 = raw.valid[1];
+			// the X tile for part B and for the anchor-gradient pass below
 #pragma unroll
-					for (int c = 0; c < 7; c++) sr[c] = OUT4[(2 * k + 7 * j + c) * kNA + aa];
+			for (int q = 0; q < 2; q++) {
+				float *xr = X + (g + 8 * q) * kSX;
 #pragma unroll
-					for (int c = 0; c < 3; c++) {
-						if (a.d_color) {
-							const float s = sigmoidf_(OUT4[(9 * k + 3 * j + c) * kNA + aa]);
-							d_col[c] = __ldg(a.d_color + p * 3 + c) * s * (1.f - s);
-						}
-						if (a.d_scaling) {
-							const float s = sigmoidf_(sr[c]);
-							const float gsc = __ldg(a.d_scaling + p * 3 + c);
-							d_sr[c] = gsc * __ldg(gs + 3 + c) * s * (1.f - s);
-							pp[6 + c] = gsc * s;                      // d get_scaling[:, 3 + c]
-						}
-						if (a.d_xyz) {
-							dxyz[c] = __ldg(a.d_xyz + p * 3 + c);
-							pp[c] = dxyz[c];                          // d anchor
-							pp[3 + c] = dxyz[c] * __ldg(off + c);     // d get_scaling[:, c]
-						}
-					}
-					if (a.d_rot) {
-						// r = v / max(|v|, eps):  dv = (g - r (r . g)) / max(|v|, eps)   (|v| > eps branch; below it dv = g / eps)
-						const float n2 = sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6];
-						const float nrm = sqrtf(n2);
-						float gr[4], dot = 0.f;
-#pragma unroll
-						for (int c = 0; c < 4; c++) {
-							gr[c] = __ldg(a.d_rot + p * 4 + c);
-							dot += gr[c] * sr[3 + c];
-						}
-						if (nrm > 1e-12f) {
-#pragma unroll
-							for (int c = 0; c < 4; c++) d_sr[3 + c] = (gr[c] - sr[3 + c] * dot / n2) / nrm;
-						} else {
-#pragma unroll
-							for (int c = 0; c < 4; c++) d_sr[3 + c] = gr[c] / 1e-12f;
-						}
-					}
-					if (a.d_xyz) {
-#pragma unroll
-						for (int c = 0; c < 3; c++) a.g_offset[((size_t)aid * k + j) * 3 + c] = dxyz[c] * __ldg(gs + c);
-					}
+				for (int c = 0; c < 4; c++) {
+					xr[8 * t + c] = f4c(raw.f[q][0], c);
+					xr[8 * t + 4 + c] = f4c(raw.f[q][1], c);
 				}
-				d_op = g_op * (1.f - nop * nop);
+				xr[32 + t] = x.xa[4][q];
+				if (t == 0) xr[40] = __int_as_float(raw.valid[q] ? raw.id[q] : -1);
+			}
+			fetch_tile(raw, tile + gridDim.x * tiles, ntiles, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, g, t);
+			uint32_t relu[2] = {0u, 0u};        // bit (16 (m & 1) + 4 nt + e) of relu[m >> 1]: H[m] fragment element > 0
+#pragma unroll
+			for (int m = 0; m < 4; m++) {
+				float h[4][4];
+				layer1_forward(h, x, sm, pl, m, lane, t);
+#pragma unroll
+				for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+					for (int e = 0; e < 4; e++)
+						if (h[nt][e] > 0.f) relu[m >> 1] |= 1u << (16 * (m & 1) + 4 * nt + e);
+				layer2_forward(h, sm, pl, OUT, S, cp.cb[m], out_count(m, k), lane, g, t);
 			}
 			__syncwarp();
-			if (on) {
-				// gradients of the pre-activations replace the pre-activations (all reads of this pair's slots are done)
-				OUT4[j * kNA + aa] = d_op;
-				OUT4[(k + j) * kNA + aa] = d_unc;
+
+			// ---- output activations backward; lanes = (anchor, offset) pairs ----------------------------------------
+			for (int idx0 = 0; idx0 < kTile * k; idx0 += 32) {
+				const int idx = idx0 + lane;
+				const bool on = idx < kTile * k;
+				const int aa = on ? idx / k : 0, j = on ? idx - aa * k : 0;
+				const int r = tile * kTile + aa;
+				const bool valid = on && r < n_vis;
+				float *row = OUT + aa * S;
+				float d_op = 0.f, d_unc = 0.f, d_col[3] = {0.f, 0.f, 0.f}, d_sr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+				float pp[kPP] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+				if (valid) {
+					const uint32_t bits = __ldg(a.f.maskbits + r);
+					const bool keep = (bits >> j) & 1u;
+					const int aid = a.f.vis_ids ? (int)__ldg(a.f.vis_ids + r) : r;
+					const float nop = tanhf(row[j]);
+					float g_op = a.d_neural_opacity ? __ldg(a.d_neural_opacity + (size_t)r * k + j) : 0.f;
+					float dxyz[3] = {0.f, 0.f, 0.f};
+					if (keep) {
+						const size_t p = (size_t)(__ldg(a.f.gauss_incl + r) - (uint32_t)__popc(bits)) + __popc(bits & ((1u << j) - 1u));
+						const float *gs = a.f.scaling + (size_t)aid * 6;
+						const float *off = a.f.offset + ((size_t)aid * k + j) * 3;
+						if (a.d_opacity) g_op += __ldg(a.d_opacity + p);
+						if (a.d_uncertainty) {
+							const float s = sigmoidf_(row[cU + j]);
+							d_unc = __ldg(a.d_uncertainty + p) * s * (1.f - s);
+						}
+						float sr[7];
 #pragma unroll
-				for (int c = 0; c < 7; c++) OUT4[(2 * k + 7 * j + c) * kNA + aa] = d_sr[c];
+						for (int c = 0; c < 7; c++) sr[c] = row[cC + 7 * j + c];
 #pragma unroll
-				for (int c = 0; c < 3; c++) OUT4[(9 * k + 3 * j + c) * kNA + aa] = d_col[c];
+						for (int c = 0; c < 3; c++) {
+							if (a.d_color) {
+								const float s = sigmoidf_(row[cR + 3 * j + c]);
+								d_col[c] = __ldg(a.d_color + p * 3 + c) * s * (1.f - s);
+							}
+							if (a.d_scaling) {
+								const float s = sigmoidf_(sr[c]);
+								const float gsc = __ldg(a.d_scaling + p * 3 + c);
+								d_sr[c] = gsc * __ldg(gs + 3 + c) * s * (1.f - s);
+								pp[6 + c] = gsc * s;                      // d get_scaling[:, 3 + c]
+							}
+							if (a.d_xyz) {
+								dxyz[c] = __ldg(a.d_xyz + p * 3 + c);
+								pp[c] = dxyz[c];                          // d anchor
+								pp[3 + c] = dxyz[c] * __ldg(off + c);     // d get_scaling[:, c]
+							}
+						}
+						if (a.d_rot) {
+							// r = v / max(|v|, eps):  dv = (g - r (r . g)) / max(|v|, eps)   (|v| > eps branch; below it dv = g / eps)
+							const float n2 = sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6];
+							const float nrm = sqrtf(n2);
+							float gr[4], dot = 0.f;
 #pragma unroll
-				for (int c = 0; c < 9; c++) PP[(aa * k + j) * 10 + c] = pp[c];
+							for (int c = 0; c < 4; c++) {
+								gr[c] = __ldg(a.d_rot + p * 4 + c);
+								dot += gr[c] * sr[3 + c];
+							}
+							if (nrm > 1e-12f) {
+#pragma unroll
+								for (int c = 0; c < 4; c++) d_sr[3 + c] = (gr[c] - sr[3 + c] * dot / n2) / nrm;
+							} else {
+#pragma unroll
+								for (int c = 0; c < 4; c++) d_sr[3 + c] = gr[c] / 1e-12f;
+							}
+						}
+						if (a.d_xyz) {
+#pragma unroll
+							for (int c = 0; c < 3; c++) a.g_offset[((size_t)aid * k + j) * 3 + c] = dxyz[c] * __ldg(gs + c);
+						}
+					}
+					d_op = g_op * (1.f - nop * nop);
+				}
+				__syncwarp();
+				if (on) {
+					// gradients of the pre-activations replace the pre-activations (all reads of this pair's slots are done)
+					row[j] = d_op;
+					row[cU + j] = d_unc;
+#pragma unroll
+					for (int c = 0; c < 7; c++) row[cC + 7 * j + c] = d_sr[c];
+#pragma unroll
+					for (int c = 0; c < 3; c++) row[cR + 3 * j + c] = d_col[c];
+#pragma unroll
+					for (int c = 0; c < kPP; c++) PP[idx * kPP + c] = pp[c];
+				}
+			}
+			__syncwarp();
+
+			// ---- layer 2 backward (gated by the relu of layer 1), layer 1 backward: registers ----------------------------
+			float dx[5][4];
+#pragma unroll
+			for (int nt = 0; nt < 5; nt++) dx[nt][0] = dx[nt][1] = dx[nt][2] = dx[nt][3] = 0.f;
+#pragma unroll
+			for (int m = 0; m < 4; m++) {
+				float dh[4][4];
+				layer2_backward(dh, sm, pl, OUT, S, cp.cb[m], out_count(m, k), lane, g, t);
+#pragma unroll
+				for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+					for (int e = 0; e < 4; e++)
+						if (!((relu[m >> 1] >> (16 * (m & 1) + 4 * nt + e)) & 1u)) dh[nt][e] = 0.f;
+				layer1_backward(dx, dh, sm, pl, m, lane);
+			}
+			// d feat: lane t holds features 8t .. 8t+7 of rows g (c0, c1) and g+8 (c2, c3)
+			if (v0) {
+				float4 *o = reinterpret_cast<float4 *>(a.g_feat + (size_t)id0 * kHid + 8 * t);
+				o[0] = make_float4(dx[0][0], dx[0][1], dx[1][0], dx[1][1]);
+				o[1] = make_float4(dx[2][0], dx[2][1], dx[3][0], dx[3][1]);
+			}
+			if (v1) {
+				float4 *o = reinterpret_cast<float4 *>(a.g_feat + (size_t)id1 * kHid + 8 * t);
+				o[0] = make_float4(dx[0][2], dx[0][3], dx[1][2], dx[1][3]);
+				o[1] = make_float4(dx[2][2], dx[2][3], dx[3][2], dx[3][3]);
+			}
+			// gradients of (ux, uy, uz, dist): tile 4, columns 0..3 = lanes t < 2
+			if (t < 2) {
+				X[g * kSX + 36 + 2 * t] = dx[4][0];
+				X[g * kSX + 37 + 2 * t] = dx[4][1];
+				X[(g + 8) * kSX + 36 + 2 * t] = dx[4][2];
+				X[(g + 8) * kSX + 37 + 2 * t] = dx[4][3];
+			}
+			__syncwarp();
+			// d anchor (3) and d get_scaling (6) per anchor: lanes = (anchor, component)
+			for (int idx = lane; idx < kTile * kPP; idx += 32) {
+				const int aa = idx / kPP, c = idx - aa * kPP;
+				const float *xr = X + aa * kSX;
+				const int id = __float_as_int(xr[40]);
+				if (id < 0) continue;
+				// sum this anchor's per-offset partials: [0..2] d anchor (from xyz), [3..8] d get_scaling
+				float s = 0.f;
+				for (int j = 0; j < k; j++) s += PP[(aa * k + j) * kPP + c];
+				if (c < 3) {
+					// view / distance path (gaussian_renderer/__init__.py:31-35): v = anchor - cam, dist = |v|, u = v / dist
+					const float ux = xr[32], uy = xr[33], uz = xr[34], dist = xr[35];
+					const float gux = xr[36], guy = xr[37], guz = xr[38], gdist = xr[39];
+					const float u = c == 0 ? ux : c == 1 ? uy : uz;
+					const float gu = c == 0 ? gux : c == 1 ? guy : guz;
+					const float udot = ux * gux + uy * guy + uz * guz;
+					s += (gu - u * udot) / dist + u * gdist;
+					a.g_anchor[(size_t)id * 3 + c] = s;
+				} else {
+					a.g_scaling[(size_t)id * 6 + (c - 3)] = s;
+				}
 			}
 		}
-		__syncwarp();
+		__syncthreads(); // every tile's X / dOUT of this CTA iteration is complete
 
-		// ---- layer 2 backward: lane = h.  dh[m][a] = sum_{o in m} W2[o][h] dout[o][a], gated by relu -----------------
+		// ==================================================== part B ====================================================
+		const int live = min(tiles, ntiles - first);              // tiles of this iteration that exist (<= 0: none)
+		for (int q = 0; q < 2 * live; q++) {
+			const float *Xt = sm + pl.warp0 + (q >> 1) * pl.per_warp + pl.x + (q & 1) * 8 * kSX;
+			const float *Dt = sm + pl.warp0 + (q >> 1) * pl.per_warp + pl.out + (q & 1) * 8 * S;
+			// H^T = relu(W1 x^T + b1): rows h = 16hh + g (+8), columns = anchors 2t (+1) of this n-tile
+			float hT[4] = {b1lo, b1lo, b1hi, b1hi};
 #pragma unroll
-		for (int m = 0; m < 4; m++) {
-			float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-			const int ob = out_base(m, k), oe = ob + out_count(m, k);
-			for (int o = ob; o < oe; o++) {
-				const float w = sm[pl.w2 + lane * pl.os + o];
-				const float4 dv = *reinterpret_cast<const float4 *>(OUT4 + o * kNA);
-				d0 = fmaf(w, dv.x, d0);
-				d1 = fmaf(w, dv.y, d1);
-				d2 = fmaf(w, dv.z, d2);
-				d3 = fmaf(w, dv.w, d3);
+			for (int ks = 0; ks < 5; ks++) {
+				const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w1f + (((mB * 5 + ks) * 2 + hh) * 32 + lane) * 4);
+				const AFrag wa = make_a(e.x, e.z, e.y, e.w);
+				const float *xr = Xt + g * kSX;
+				const float xb0 = ks < 4 ? xr[8 * t + ks] : xr[32 + t];
+				const float xb1 = ks < 4 ? xr[8 * t + 4 + ks] : 0.f;
+				mma3(hT, wa, xb0, xb1);
 			}
-			const float4 hv = *reinterpret_cast<const float4 *>(H4 + (m * kHStride + lane) * kNA);
-			*reinterpret_cast<float4 *>(DH4 + (m * kHStride + lane) * kNA) =
-			    make_float4(hv.x > 0.f ? d0 : 0.f, hv.y > 0.f ? d1 : 0.f, hv.z > 0.f ? d2 : 0.f, hv.w > 0.f ? d3 : 0.f);
-		}
-		__syncwarp();
-
-		// ---- layer 1 backward: lane = input i (and input 32 + (lane & 3) in a second set) ----------------------------
-		{
-			float dx[kNA] = {0.f, 0.f, 0.f, 0.f}, de[kNA] = {0.f, 0.f, 0.f, 0.f};
-			const int ie = kHid + (lane & 3);
-			for (int mh = 0; mh < 4 * kHid; mh++) {
-				const int m = mh >> 5, h = mh & 31;
-				const float w = sm[pl.w1 + (m * kIn + lane) * kW1Stride + h];
-				const float we = sm[pl.w1 + (m * kIn + ie) * kW1Stride + h];
-				const float4 dv = *reinterpret_cast<const float4 *>(DH4 + (m * kHStride + h) * kNA);
-				dx[0] = fmaf(w, dv.x, dx[0]); dx[1] = fmaf(w, dv.y, dx[1]); dx[2] = fmaf(w, dv.z, dx[2]); dx[3] = fmaf(w, dv.w, dx[3]);
-				de[0] = fmaf(we, dv.x, de[0]); de[1] = fmaf(we, dv.y, de[1]); de[2] = fmaf(we, dv.z, de[2]); de[3] = fmaf(we, dv.w, de[3]);
+			// dH^T = W2^T dOUT^T, gated
+			float dT[4] = {0.f, 0.f, 0.f, 0.f};
+			for (int ks = 0; ks < nksB; ks++) {
+				const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w2b + (((cbB >> 3) + ks) * 2 + hh) * 128 + lane * 4);
+				const AFrag wa = make_a(e.x, e.z, e.y, e.w);
+				const float *dr = Dt + g * S + cbB + 8 * ks + t;
+				mma3(dT, wa, dr[0], dr[4]);
 			}
 #pragma unroll
-			for (int aa = 0; aa < kNA; aa++) {
-				// view / distance path (gaussian_renderer/__init__.py:31-35): v = anchor - cam, dist = |v|, u = v / dist
-				const float gux = __shfl_sync(0xffffffffu, de[aa], 0), guy = __shfl_sync(0xffffffffu, de[aa], 1);
-				const float guz = __shfl_sync(0xffffffffu, de[aa], 2), gdist = __shfl_sync(0xffffffffu, de[aa], 3);
-				if (!io.valid[aa] || g >= groups) continue;
-				a.g_feat[(size_t)io.id[aa] * kHid + lane] = dx[aa];
-				if (lane < 9) {
-					// sum this anchor's per-offset partials: [0..2] d anchor (from xyz), [3..8] d get_scaling
-					float s = 0.f;
-					for (int j = 0; j < k; j++) s += PP[(aa * k + j) * 10 + lane];
-					if (lane < 3) {
-						const float u = lane == 0 ? io.ux[aa] : lane == 1 ? io.uy[aa] : io.uz[aa];
-						const float gu = lane == 0 ? gux : lane == 1 ? guy : guz;
-						const float udot = io.ux[aa] * gux + io.uy[aa] * guy + io.uz[aa] * guz;
-						s += (gu - u * udot) / io.dist[aa] + u * gdist;
-						a.g_anchor[(size_t)io.id[aa] * 3 + lane] = s;
-					} else {
-						a.g_scaling[(size_t)io.id[aa] * 6 + (lane - 3)] = s;
+			for (int e = 0; e < 4; e++) {
+				if (!(hT[e] > 0.f)) dT[e] = 0.f;
+				hT[e] = fmaxf(hT[e], 0.f);
+			}
+			accb1[0] += dT[0] + dT[1];
+			accb1[1] += dT[2] + dT[3];
+			// dW1 += dH^T x   (A = the dT fragment, contraction = the 8 anchors; B from the X tile)
+			{
+				const AFrag da = c_as_a(dT);
+				const float *x0 = Xt + (2 * t) * kSX + g, *x1 = x0 + kSX;
+#pragma unroll
+				for (int nt = 0; nt < 5; nt++) mma3(acc1[nt], da, x0[8 * nt], x1[8 * nt]);
+			}
+			// dW2 += dOUT^T H   (A from the dOUT tile: rows o = 16mt + g (+8), contraction = anchors; B = the hT fragment)
+			{
+				const float *d0 = Dt + (2 * t) * S + cbB + g, *d1 = d0 + S;
+#pragma unroll
+				for (int mt = 0; mt < KMT; mt++) {
+					if (mt < nmtB) {
+						const float a0 = d0[16 * mt], a1 = d0[16 * mt + 8], a2 = d1[16 * mt], a3 = d1[16 * mt + 8];
+						const AFrag oa = make_a(a0, a1, a2, a3);
+						mma3(acc2[mt][0], oa, hT[0], hT[1]);
+						mma3(acc2[mt][1], oa, hT[2], hT[3]);
+						accb2[mt][0] += a0 + a2;
+						accb2[mt][1] += a1 + a3;
 					}
 				}
 			}
 		}
-		__syncthreads(); // every warp's X4 / H4 / DH4 / DOUT4 of this CTA iteration are complete
-
-		// ---- weight gradients: each thread owns a slice, loops over the CTA's 8 groups ------------------------------
-		for (int w = 0; w < kWarps; w++) {
-			const float *wb = sm + pl.warp0 + w * pl.per_warp;
-			const float4 dh = *reinterpret_cast<const float4 *>(wb + pl.dh4 + (m1 * kHStride + lane) * kNA);
-			if (half == 0) accb1 += (dh.x + dh.y) + (dh.z + dh.w);
-#pragma unroll
-			for (int q = 0; q < 18; q++) {
-				const float4 x = *reinterpret_cast<const float4 *>(wb + pl.x4 + (18 * half + q) * kNA);
-				acc1[q] = fmaf(dh.x, x.x, fmaf(dh.y, x.y, fmaf(dh.z, x.z, fmaf(dh.w, x.w, acc1[q]))));
-			}
-			const float4 hv = *reinterpret_cast<const float4 *>(wb + pl.h4 + (m2 * kHStride + lane) * kNA);
-#pragma unroll
-			for (int q = 0; q < kAcc2; q++) {
-				if (q < o_cnt) {
-					const float4 dv = *reinterpret_cast<const float4 *>(wb + pl.out4 + (o_first + q) * kNA);
-					acc2[q] = fmaf(hv.x, dv.x, fmaf(hv.y, dv.y, fmaf(hv.z, dv.z, fmaf(hv.w, dv.w, acc2[q]))));
-				}
-			}
-			if (lane < o_cnt) {
-				const float4 dv = *reinterpret_cast<const float4 *>(wb + pl.out4 + (o_first + lane) * kNA);
-				accb2 += (dv.x + dv.y) + (dv.z + dv.w);
-			}
-		}
-		__syncthreads(); // slices consumed before the next iteration overwrites the activations
+		__syncthreads(); // tiles consumed before the next iteration overwrites them
 	}
 
 	// ---- flush: one atomic per owned entry (torch layouts: w1[h][i], b1[h], w2[o][h], b2[o]) ---------------------
 #pragma unroll
-	for (int q = 0; q < 18; q++) atomicAdd(a.g_w1[m1] + lane * kIn + 18 * half + q, acc1[q]);
-	if (half == 0) atomicAdd(a.g_b1[m1] + lane, accb1);
+	for (int nt = 0; nt < 5; nt++)
 #pragma unroll
-	for (int q = 0; q < kAcc2; q++)
-		if (q < o_cnt) atomicAdd(a.g_w2[m2] + (o_first + q - out_base(m2, k)) * kHid + lane, acc2[q]);
-	if (lane < o_cnt) atomicAdd(a.g_b2[m2] + (o_first + lane - out_base(m2, k)), accb2);
+		for (int e = 0; e < 4; e++) {
+			const int h = 16 * hh + g + 8 * (e >> 1), i = 8 * nt + 2 * t + (e & 1);
+			if (i < kIn) atomicAdd(a.g_w1[mB] + h * kIn + i, acc1[nt][e]);
+		}
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		float v = accb1[q];
+		v += __shfl_xor_sync(kFull, v, 1);
+		v += __shfl_xor_sync(kFull, v, 2);
+		if (t == 0) atomicAdd(a.g_b1[mB] + 16 * hh + g + 8 * q, v);
+	}
+#pragma unroll
+	for (int mt = 0; mt < KMT; mt++) {
+		if (mt < nmtB) {
+#pragma unroll
+			for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const int o = 16 * mt + g + 8 * (e >> 1), h = 16 * hh + 8 * nt + 2 * t + (e & 1);
+					if (o < nB) atomicAdd(a.g_w2[mB] + o * kHid + h, acc2[mt][nt][e]);
+				}
+#pragma unroll
+			for (int q = 0; q < 2; q++) {
+				float v = accb2[mt][q];
+				v += __shfl_xor_sync(kFull, v, 1);
+				v += __shfl_xor_sync(kFull, v, 2);
+				const int o = 16 * mt + g + 8 * q;
+				if (hh == 0 && t == 0 && o < nB) atomicAdd(a.g_b2[mB] + o, v);
+			}
+		}
+	}
 }
 
 // ---- densification statistics (scene/gaussian_model.py:729-757, GaussianModel.training_statis) --------------------------------
@@ -586,10 +818,11 @@ __global__ void compact_visible_kernel(int A, const uint32_t *__restrict__ flags
 	if (i < A && flags[i]) ids[incl[i] - 1] = (uint32_t)i;
 }
 
-// persistent CTAs per SM of the two forward kernels (72 KB of shared memory and 64 registers each: three fit)
+// persistent CTAs per SM of the two forward kernels (<= 100 KB of shared memory and <= 128 registers each)
 #ifndef GSR_DEC_FWD_CTAS
-#define GSR_DEC_FWD_CTAS 3
+#define GSR_DEC_FWD_CTAS 2
 #endif
+constexpr size_t kMaxSmemBytes = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
 int sm_count()
 {
@@ -602,11 +835,11 @@ int sm_count()
 	}
 	return sms;
 }
-// persistent grid: enough CTAs to cover the groups, at most `per_sm` per SM
-int grid_for(int anchors, int per_sm)
+// persistent grid: enough CTAs to cover the tiles (`tiles` per CTA iteration), at most `per_sm` per SM
+int grid_for(int anchors, int per_sm, int tiles)
 {
-	const int groups = (anchors + kNA - 1) / kNA;
-	const int want = (groups + kWarps - 1) / kWarps;
+	const int ntiles = (anchors + kTile - 1) / kTile;
+	const int want = (ntiles + tiles - 1) / tiles;
 	return max(1, min(want, per_sm * sm_count()));
 }
 
@@ -653,9 +886,9 @@ cudaError_t decode_stage1(int A, int k, const float *anchor, const float *feat, 
 	a.vis_ids = visible_mask ? ids : nullptr;
 	a.anchor = anchor; a.feat = feat; a.campos = campos; a.wt = wt;
 	a.neural_opacity = neural_opacity; a.mask = mask; a.count = count; a.maskbits = bits;
-	const size_t smem = (size_t)smem_plan(k, false).total * 4;
+	const size_t smem = (size_t)smem_plan(k, 0, 1, false, kWarps).total * 4;
 	if ((e = set_smem(decode_opacity_kernel, smem)) != cudaSuccess) return e;
-	decode_opacity_kernel<<<grid_for(A, GSR_DEC_FWD_CTAS), 256, smem, stream>>>(a);
+	decode_opacity_kernel<<<grid_for(A, GSR_DEC_FWD_CTAS, kWarps), 256, smem, stream>>>(a);
 	count_launch(2);
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if ((e = inclusive_sum_gather(count, nullptr, gincl, A, scratch + L.scan_tmp, stream)) != cudaSuccess) return e;
@@ -669,9 +902,9 @@ cudaError_t decode_stage1(int A, int k, const float *anchor, const float *feat, 
 cudaError_t decode_stage2(const DecodeArgs &a, cudaStream_t stream)
 {
 	cudaError_t e;
-	const size_t smem = (size_t)smem_plan(a.k, false).total * 4;
+	const size_t smem = (size_t)smem_plan(a.k, 1, 4, false, kWarps).total * 4;
 	if ((e = set_smem(decode_outputs_kernel, smem)) != cudaSuccess) return e;
-	decode_outputs_kernel<<<grid_for(a.n_vis, GSR_DEC_FWD_CTAS), 256, smem, stream>>>(a);
+	decode_outputs_kernel<<<grid_for(a.n_vis, GSR_DEC_FWD_CTAS, kWarps), 256, smem, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }
@@ -679,10 +912,19 @@ cudaError_t decode_stage2(const DecodeArgs &a, cudaStream_t stream)
 cudaError_t decode_backward(const DecodeBwdArgs &a, cudaStream_t stream)
 {
 	cudaError_t e;
-	const size_t smem = (size_t)smem_plan(a.f.k, true).total * 4;
-	if ((e = set_smem(decode_backward_kernel, smem)) != cudaSuccess) return e;
-	// persistent; 2 CTAs/SM (102 KB of shared memory each at k = 10, 128 registers)
-	decode_backward_kernel<<<grid_for(a.f.n_vis, 2), 256, smem, stream>>>(a);
+	// persistent, one CTA per SM.  Eight tiles (128 anchors) per CTA iteration while their X / OUT / partial tiles fit next to
+	// the four weight copies (k <= 10: 217 KB), four above that.
+	const int tiles = (size_t)smem_plan(a.f.k, 0, 4, true, kWarps).total * 4 <= kMaxSmemBytes ? kWarps : kWarps / 2;
+	const size_t smem = (size_t)smem_plan(a.f.k, 0, 4, true, tiles).total * 4;
+	if (smem > kMaxSmemBytes) return cudaErrorInvalidConfiguration;
+	const int grid = grid_for(a.f.n_vis, 1, tiles);
+	if ((7 * a.f.k + 15) / 16 <= 5) {
+		if ((e = set_smem(decode_backward_kernel<5>, smem)) != cudaSuccess) return e;
+		decode_backward_kernel<5><<<grid, 256, smem, stream>>>(a, tiles);
+	} else {
+		if ((e = set_smem(decode_backward_kernel<(7 * kDecMaxK + 15) / 16>, smem)) != cudaSuccess) return e;
+		decode_backward_kernel<(7 * kDecMaxK + 15) / 16><<<grid, 256, smem, stream>>>(a, tiles);
+	}
 	count_launch();
 	return cudaGetLastError();
 }

@@ -4,7 +4,7 @@
 
 namespace gsr {
 
-constexpr int kDecNA = 4;     // anchors decoded together by one warp
+constexpr int kDecNA = 16;    // anchors per warp tile (the M dimension of the MLP products)
 constexpr int kDecMaxK = 16;  // largest supported n_offsets
 
 // The four MLPs of scene/gaussian_model.py:118-144 in torch.nn.Linear layout (weight[out][in], bias[out]):

@@ -170,7 +170,8 @@ GSR_API int gsr_mark_visible(
  *   mlp_params: HOST array of 16 device pointers, torch.nn.Linear layout, in the order
  *               {opacity, uncertainty, cov, colour} x {w1[32,36], b1[32], w2[n_out,32], b2[n_out]}, n_out = k, k, 7k, 3k
  *   scratch: gsr_decode_scratch_bytes(A) bytes; written by stage 1, read by stage 2 and by the backward.
- * feat_dim must be 32 and 1 <= n_offsets <= 16 (gsr_decode_supported), else GSR_E_BADARG.
+ * feat_dim must be 32 and 1 <= n_offsets <= 16 (gsr_decode_supported), else GSR_E_BADARG; anchor_feat and g_feat must be
+ * 16-byte aligned (rows are moved as float4), else GSR_E_BADARG.
  *
  * Stage 1: neural_opacity[A*k] (tanh of the opacity MLP, rows of visible anchors in order, first n_vis*k entries valid),
  *          mask[A*k] (neural_opacity > 0), counts_host (PINNED int64[2], pre-zeroed by the callee): [0] n_vis, [1] P.
