@@ -50,7 +50,9 @@ constexpr int kPP = 9;            // per (anchor, offset) partials: d anchor (3)
 constexpr unsigned kFull = 0xffffffffu;
 
 __host__ __device__ inline int out_count(int m, int k) { return m == 0 ? k : m == 1 ? k : m == 2 ? 7 * k : 3 * k; }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + e^-x) with the SFU exponential (ex2.approx on x log2 e: relative error ~1e-6 at |x| = 20, i.e. <= 3e-7 absolute on
+// the sigmoid — the parity bound of the decode is 2e-5) and a correctly rounded reciprocal
+__device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 // Column plan of the OUT tile for the MLPs [m0, m1): each MLP padded to a multiple of 16 columns (pad columns hold zeros),
 // row stride S = cols + 4 (S = 4 mod 8 with S/4 odd: the fragment loads of parts A and B are bank-conflict free).
@@ -72,8 +74,9 @@ __host__ __device__ inline ColPlan col_plan(int k, int m0, int m1)
 
 // shared-memory carve-up (in floats)
 struct SmemPlan {
-	int w1f, w2f, w1b, w2b, b1, b2, warp0, per_warp, out, x, pp, total;
+	int w1f, w2f, w1b, w2b, b1, b2, warp0, per_warp, out, tab, x, pp, total;
 };
+constexpr int kTab = 12;          // per-anchor table row: id, mask bits, first output row, anchor xyz (3), get_scaling (6)
 __host__ __device__ inline SmemPlan smem_plan(int k, int m0, int m1, bool backward, int tiles)
 {
 	const ColPlan cp = col_plan(k, m0, m1);
@@ -90,6 +93,7 @@ __host__ __device__ inline SmemPlan smem_plan(int k, int m0, int m1, bool backwa
 	p.warp0 = off;
 	int w = 0;
 	p.out = w;  w += kTile * cp.S;
+	p.tab = w;  if (m1 > 1) w += kTile * kTab;
 	p.x = w;    if (backward) w += kTile * kSX;
 	p.pp = w;   if (backward) w += kTile * k * kPP;
 	w = (w + 3) & ~3;
@@ -106,7 +110,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
-	asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
 	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
 	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -134,6 +138,22 @@ __device__ __forceinline__ void mma3(float (&c)[4], const AFrag &a, float b0, fl
 	mma_tf32(c, a.hi, b0l, b1l);
 	mma_tf32(c, a.hi, b0h, b1h);
 }
+// The same with the two correction products in an accumulator of their own (c + d is the result): dependent HMMAs are
+// issued back to back otherwise, and a chain of them — 3 per k-step — is what a warp waits on in the short products.
+__device__ __forceinline__ void mma3(float (&c)[4], float (&d)[4], const AFrag &a, float b0, float b1)
+{
+	uint32_t b0h, b0l, b1h, b1l;
+	split_tf32(b0, b0h, b0l);
+	split_tf32(b1, b1h, b1l);
+	mma_tf32(c, a.hi, b0h, b1h);
+	mma_tf32(d, a.lo, b0h, b1h);
+	mma_tf32(d, a.hi, b0l, b1l);
+}
+__device__ __forceinline__ void zero4(float (&c)[4]) { c[0] = c[1] = c[2] = c[3] = 0.f; }
+__device__ __forceinline__ void add4(float (&c)[4], const float (&d)[4])
+{
+	c[0] += d[0]; c[1] += d[1]; c[2] += d[2]; c[3] += d[3];
+}
 __device__ __forceinline__ float f4c(const float4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
 // ---- input-slot maps ---------------------------------------------------------------------------------------------------------
@@ -151,45 +171,67 @@ __host__ __device__ inline int in1b(int nt, int c) { return nt < 4 ? 8 * (c >> 1
 //   W2B[tile8][p][lane][4]   (b0, b1) of n-tiles 2p, 2p+1:    b0 = W2[m][8ks+t][8nt+g]          b1 = W2[m][8ks+t+4][8nt+g]
 // (tile8 = (cb[m] / 8) + tile index inside MLP m; rows o >= out_count(m) are zeros).  W1F and W2B double as the A operands of
 // part B: read as (a0, a2, a1, a3) of the 16 hidden units 16p .. 16p+15.
+// Loads go out in batches of eight per thread before the first store (a load -> store loop would pay the L2 latency once per
+// element: 15 to 76 elements per thread).
+template <typename F>
+__device__ __forceinline__ void fill_smem(float *dst, int n, int tid, F value_of)
+{
+	for (int base = tid; base < n; base += 256 * 8) {
+		float v[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const int idx = base + 256 * u;
+			v[u] = idx < n ? value_of(idx) : 0.f;
+		}
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const int idx = base + 256 * u;
+			if (idx < n) dst[idx] = v[u];
+		}
+	}
+}
 __device__ __forceinline__ void load_weights(float *sm, const SmemPlan &pl, const ColPlan &cp, const DecodeWeights &wt, int k, int m0, int m1,
                                              bool backward, int tid)
 {
 	const int nm = m1 - m0;
-	for (int idx = tid; idx < nm * 1280; idx += 256) {
+	fill_smem(sm + pl.w1f, nm * 1280, tid, [&](int idx) {
 		const int e = idx & 3, lane = (idx >> 2) & 31, g = lane >> 2, t = lane & 3;
-		{   // W1F
-			const int p = (idx >> 7) & 1, ks = (idx >> 8) % 5, m = m0 + idx / 1280;
-			const int nt = 2 * p + (e >> 1), i = in1(ks, t + 4 * (e & 1));
-			sm[pl.w1f + idx] = i < 0 ? 0.f : __ldg(wt.w1[m] + (8 * nt + g) * kIn + i);
-		}
-		if (backward) {   // W1B
+		const int p = (idx >> 7) & 1, ks = (idx >> 8) % 5, m = m0 + idx / 1280;
+		const int nt = 2 * p + (e >> 1), i = in1(ks, t + 4 * (e & 1));
+		return i < 0 ? 0.f : __ldg(wt.w1[m] + (8 * nt + g) * kIn + i);
+	});
+	if (backward)
+		fill_smem(sm + pl.w1b, nm * 1280, tid, [&](int idx) {
+			const int e = idx & 3, lane = (idx >> 2) & 31, g = lane >> 2, t = lane & 3;
 			const int nt = (idx >> 7) % 5, ksp = ((idx >> 7) / 5) & 1, m = m0 + idx / 1280;
 			const int h = 8 * (2 * ksp + (e >> 1)) + 2 * t + (e & 1), i = in1b(nt, g);
-			sm[pl.w1b + idx] = i < 0 ? 0.f : __ldg(wt.w1[m] + h * kIn + i);
-		}
-	}
-	for (int idx = tid; idx < cp.cols * 32; idx += 256) {
-		const int e = idx & 3, lane = (idx >> 2) & 31, g = lane >> 2, t = lane & 3;
-		const int q = (idx >> 7) & 1, tile8 = idx >> 8;
+			return i < 0 ? 0.f : __ldg(wt.w1[m] + h * kIn + i);
+		});
+	auto mlp_of_tile = [&](int tile8) {
 		int m = m0;
 		while (m + 1 < m1 && cp.cb[m + 1] <= 8 * tile8) m++;
-		const int tl = tile8 - cp.cb[m] / 8, n_m = out_count(m, k);
-		{   // W2F: q = ksp
-			const int o = 8 * tl + g, h = 8 * (2 * q + (e >> 1)) + 2 * t + (e & 1);
-			sm[pl.w2f + idx] = o < n_m ? __ldg(wt.w2[m] + o * kHid + h) : 0.f;
-		}
-		if (backward) {   // W2B: q = p
-			const int o = 8 * tl + t + 4 * (e & 1), h = 8 * (2 * q + (e >> 1)) + g;
-			sm[pl.w2b + idx] = o < n_m ? __ldg(wt.w2[m] + o * kHid + h) : 0.f;
-		}
-	}
-	for (int idx = tid; idx < nm * kHid; idx += 256) sm[pl.b1 + idx] = __ldg(wt.b1[m0 + (idx >> 5)] + (idx & 31));
-	for (int c = tid; c < cp.cols + 8; c += 256) {
+		return m;
+	};
+	fill_smem(sm + pl.w2f, cp.cols * 32, tid, [&](int idx) {   // q = ksp
+		const int e = idx & 3, lane = (idx >> 2) & 31, g = lane >> 2, t = lane & 3;
+		const int q = (idx >> 7) & 1, tile8 = idx >> 8, m = mlp_of_tile(tile8);
+		const int o = 8 * (tile8 - cp.cb[m] / 8) + g, h = 8 * (2 * q + (e >> 1)) + 2 * t + (e & 1);
+		return o < out_count(m, k) ? __ldg(wt.w2[m] + o * kHid + h) : 0.f;
+	});
+	if (backward)
+		fill_smem(sm + pl.w2b, cp.cols * 32, tid, [&](int idx) {   // q = p
+			const int e = idx & 3, lane = (idx >> 2) & 31, g = lane >> 2, t = lane & 3;
+			const int q = (idx >> 7) & 1, tile8 = idx >> 8, m = mlp_of_tile(tile8);
+			const int o = 8 * (tile8 - cp.cb[m] / 8) + t + 4 * (e & 1), h = 8 * (2 * q + (e >> 1)) + g;
+			return o < out_count(m, k) ? __ldg(wt.w2[m] + o * kHid + h) : 0.f;
+		});
+	fill_smem(sm + pl.b1, nm * kHid, tid, [&](int idx) { return __ldg(wt.b1[m0 + (idx >> 5)] + (idx & 31)); });
+	fill_smem(sm + pl.b2, cp.cols + 8, tid, [&](int c) {
 		float v = 0.f;
 		for (int m = m0; m < m1; m++)
 			if (c >= cp.cb[m] && c < cp.cb[m] + out_count(m, k)) v = __ldg(wt.b2[m] + (c - cp.cb[m]));
-		sm[pl.b2 + c] = v;
-	}
+		return v;
+	});
 }
 
 // ---- the gather ---------------------------------------------------------------------------------------------------------------
@@ -200,10 +242,15 @@ struct TileRaw {
 	bool valid[2];
 	float4 f[2][2];                 // feat[8t .. 8t+3], feat[8t+4 .. 8t+7]
 	float ax[2], ay[2], az[2];
+	uint32_t bits[2], incl[2];      // TAB: the anchor's kept-offset mask and inclusive output count (lane t == 0)
+	float gsa[2], gsb[2];           // TAB: get_scaling[t], get_scaling[4 + t] (t < 2)
 };
-__device__ __forceinline__ void fetch_tile(TileRaw &r, int tile, int ntiles, int n_vis, const uint32_t *__restrict__ vis_ids,
-                                           const float *__restrict__ anchor, const float *__restrict__ feat, int g, int t)
+// TAB: also fetch what the per-(anchor, offset) pass needs per anchor (stage 2 and the backward; stage 1 produces it)
+template <bool TAB>
+__device__ __forceinline__ void fetch_tile(TileRaw &r, int tile, int ntiles, int n_vis, const DecodeArgs &a, int g, int t)
 {
+	const uint32_t *__restrict__ vis_ids = a.vis_ids;
+	const float *__restrict__ anchor = a.anchor, *__restrict__ feat = a.feat;
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
 		const int rank = tile * kTile + g + 8 * q;
@@ -221,6 +268,37 @@ __device__ __forceinline__ void fetch_tile(TileRaw &r, int tile, int ntiles, int
 			r.ax[q] = __ldg(anchor + (size_t)r.id[q] * 3 + 0);
 			r.ay[q] = __ldg(anchor + (size_t)r.id[q] * 3 + 1);
 			r.az[q] = __ldg(anchor + (size_t)r.id[q] * 3 + 2);
+		}
+		if (TAB) {
+			r.bits[q] = r.incl[q] = 0u;
+			r.gsa[q] = r.gsb[q] = 0.f;
+			if (r.valid[q]) {
+				const int rank = tile * kTile + g + 8 * q;
+				if (t == 0) {
+					r.bits[q] = __ldg(a.maskbits + rank);
+					r.incl[q] = __ldg(a.gauss_incl + rank);
+				}
+				r.gsa[q] = __ldg(a.scaling + (size_t)r.id[q] * 6 + t);
+				if (t < 2) r.gsb[q] = __ldg(a.scaling + (size_t)r.id[q] * 6 + 4 + t);
+			}
+		}
+	}
+}
+// the per-anchor table of the tile, from the registers of the gather
+__device__ __forceinline__ void write_table(float *TAB, const TileRaw &r, int g, int t)
+{
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		float *row = TAB + (g + 8 * q) * kTab;
+		row[6 + t] = r.gsa[q];
+		if (t < 2) row[10 + t] = r.gsb[q];
+		if (t == 0) {
+			row[0] = __int_as_float(r.valid[q] ? r.id[q] : -1);
+			row[1] = __uint_as_float(r.bits[q]);
+			row[2] = __uint_as_float(r.incl[q] - (uint32_t)__popc(r.bits[q]));
+			row[3] = r.ax[q];
+			row[4] = r.ay[q];
+			row[5] = r.az[q];
 		}
 	}
 }
@@ -266,20 +344,23 @@ __device__ __forceinline__ void layer1_forward(float (&h)[4][4], const TileX &x,
 		h[nt][0] = h[nt][2] = b.x;
 		h[nt][1] = h[nt][3] = b.y;
 	}
+	float hc[4][4];
+#pragma unroll
+	for (int nt = 0; nt < 4; nt++) zero4(hc[nt]);
 #pragma unroll
 	for (int ks = 0; ks < 5; ks++) {
 		const AFrag a = make_a(x.xa[ks][0], x.xa[ks][1], x.xa[ks][2], x.xa[ks][3]);
 #pragma unroll
 		for (int p = 0; p < 2; p++) {
 			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w1f + (((ml * 5 + ks) * 2 + p) * 32 + lane) * 4);
-			mma3(h[2 * p], a, e.x, e.y);
-			mma3(h[2 * p + 1], a, e.z, e.w);
+			mma3(h[2 * p], hc[2 * p], a, e.x, e.y);
+			mma3(h[2 * p + 1], hc[2 * p + 1], a, e.z, e.w);
 		}
 	}
 #pragma unroll
 	for (int nt = 0; nt < 4; nt++)
 #pragma unroll
-		for (int e = 0; e < 4; e++) h[nt][e] = fmaxf(h[nt][e], 0.f);
+		for (int e = 0; e < 4; e++) h[nt][e] = fmaxf(h[nt][e] + hc[nt][e], 0.f);
 }
 // layer 2 of MLP m: OUT[a][cb + o] = b2[o] + sum_h W2[o][h] H[a][h], H from the C fragments of layer 1
 __device__ __forceinline__ void layer2_forward(const float (&h)[4][4], const float *sm, const SmemPlan &pl, float *OUT, int S, int cb, int n_m,
@@ -288,19 +369,30 @@ __device__ __forceinline__ void layer2_forward(const float (&h)[4][4], const flo
 	AFrag ha[4];
 #pragma unroll
 	for (int ks = 0; ks < 4; ks++) ha[ks] = c_as_a(h[ks]);
-	const int nt8 = (n_m + 7) >> 3;
-	for (int nt = 0; nt < nt8; nt++) {
-		const int col = cb + 8 * nt + 2 * t;
-		const float2 b = *reinterpret_cast<const float2 *>(sm + pl.b2 + col);
-		float acc[4] = {b.x, b.y, b.x, b.y};
+	// one 16-column block = two n-tiles per iteration (the column plan pads every MLP to whole blocks; pad tiles have zero
+	// weights and biases and produce the zeros the pad columns must hold)
+	const int nblk = (n_m + 15) >> 4;
+	for (int blk = 0; blk < nblk; blk++) {
+		const int col = cb + 16 * blk + 2 * t;
+		const float2 bA = *reinterpret_cast<const float2 *>(sm + pl.b2 + col), bB = *reinterpret_cast<const float2 *>(sm + pl.b2 + col + 8);
+		float accA[4] = {bA.x, bA.y, bA.x, bA.y}, accB[4] = {bB.x, bB.y, bB.x, bB.y}, corA[4], corB[4];
+		zero4(corA);
+		zero4(corB);
+		const float *w = sm + pl.w2f + ((cb >> 3) + 2 * blk) * 256 + lane * 4;
 #pragma unroll
 		for (int ksp = 0; ksp < 2; ksp++) {
-			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w2f + (((cb >> 3) + nt) * 2 + ksp) * 128 + lane * 4);
-			mma3(acc, ha[2 * ksp], e.x, e.y);
-			mma3(acc, ha[2 * ksp + 1], e.z, e.w);
+			const float4 eA = *reinterpret_cast<const float4 *>(w + ksp * 128), eB = *reinterpret_cast<const float4 *>(w + 256 + ksp * 128);
+			mma3(accA, corA, ha[2 * ksp], eA.x, eA.y);
+			mma3(accB, corB, ha[2 * ksp], eB.x, eB.y);
+			mma3(accA, corA, ha[2 * ksp + 1], eA.z, eA.w);
+			mma3(accB, corB, ha[2 * ksp + 1], eB.z, eB.w);
 		}
-		*reinterpret_cast<float2 *>(OUT + g * S + col) = make_float2(acc[0], acc[1]);
-		*reinterpret_cast<float2 *>(OUT + (g + 8) * S + col) = make_float2(acc[2], acc[3]);
+		add4(accA, corA);
+		add4(accB, corB);
+		*reinterpret_cast<float2 *>(OUT + g * S + col) = make_float2(accA[0], accA[1]);
+		*reinterpret_cast<float2 *>(OUT + (g + 8) * S + col) = make_float2(accA[2], accA[3]);
+		*reinterpret_cast<float2 *>(OUT + g * S + col + 8) = make_float2(accB[0], accB[1]);
+		*reinterpret_cast<float2 *>(OUT + (g + 8) * S + col + 8) = make_float2(accB[2], accB[3]);
 	}
 }
 // layer 2 backward of MLP m: dh[nt] = C fragments of dOUT[:, MLP m] W2 (rows = anchors, columns = hidden 8nt + 2t, +1), not gated
@@ -308,7 +400,10 @@ __device__ __forceinline__ void layer2_backward(float (&dh)[4][4], const float *
                                                 int lane, int g, int t)
 {
 #pragma unroll
-	for (int nt = 0; nt < 4; nt++) dh[nt][0] = dh[nt][1] = dh[nt][2] = dh[nt][3] = 0.f;
+	for (int nt = 0; nt < 4; nt++) zero4(dh[nt]);
+	float dc[4][4];
+#pragma unroll
+	for (int nt = 0; nt < 4; nt++) zero4(dc[nt]);
 	const int nks = (n_m + 7) >> 3;
 	for (int ks = 0; ks < nks; ks++) {
 		const float *r0 = OUT + g * S + cb + 8 * ks + t, *r1 = r0 + 8 * S;
@@ -316,13 +411,16 @@ __device__ __forceinline__ void layer2_backward(float (&dh)[4][4], const float *
 #pragma unroll
 		for (int p = 0; p < 2; p++) {
 			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w2b + (((cb >> 3) + ks) * 2 + p) * 128 + lane * 4);
-			mma3(dh[2 * p], a, e.x, e.y);
-			mma3(dh[2 * p + 1], a, e.z, e.w);
+			mma3(dh[2 * p], dc[2 * p], a, e.x, e.y);
+			mma3(dh[2 * p + 1], dc[2 * p + 1], a, e.z, e.w);
 		}
 	}
+#pragma unroll
+	for (int nt = 0; nt < 4; nt++) add4(dh[nt], dc[nt]);
 }
 // layer 1 backward of MLP m: dx[nt] += dh W1; afterwards lane t holds d feat[8t + 2nt + e] of rows g (c0, c1) and g+8 (c2, c3)
-__device__ __forceinline__ void layer1_backward(float (&dx)[5][4], const float (&dh)[4][4], const float *sm, const SmemPlan &pl, int ml, int lane)
+__device__ __forceinline__ void layer1_backward(float (&dx)[5][4], float (&dxc)[5][4], const float (&dh)[4][4], const float *sm, const SmemPlan &pl,
+                                                int ml, int lane)
 {
 #pragma unroll
 	for (int ksp = 0; ksp < 2; ksp++) {
@@ -330,8 +428,8 @@ __device__ __forceinline__ void layer1_backward(float (&dx)[5][4], const float (
 #pragma unroll
 		for (int nt = 0; nt < 5; nt++) {
 			const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w1b + (((ml * 2 + ksp) * 5 + nt) * 32 + lane) * 4);
-			mma3(dx[nt], a0, e.x, e.y);
-			mma3(dx[nt], a1, e.z, e.w);
+			mma3(dx[nt], dxc[nt], a0, e.x, e.y);
+			mma3(dx[nt], dxc[nt], a1, e.z, e.w);
 		}
 	}
 }
@@ -353,11 +451,11 @@ __global__ void __launch_bounds__(256, 2) decode_opacity_kernel(DecodeArgs a)
 	const int ntiles = (n_vis + kTile - 1) / kTile;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
 	TileRaw raw;
-	fetch_tile(raw, blockIdx.x * kWarps + warp, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+	fetch_tile<false>(raw, blockIdx.x * kWarps + warp, ntiles, n_vis, a, g, t);
 	for (int tile = blockIdx.x * kWarps + warp; tile < ntiles; tile += gridDim.x * kWarps) {
 		TileX x;
 		stage_tile(x, raw, cx, cy, cz, t);
-		fetch_tile(raw, tile + gridDim.x * kWarps, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+		fetch_tile<false>(raw, tile + gridDim.x * kWarps, ntiles, n_vis, a, g, t);
 		float h[4][4];
 		layer1_forward(h, x, sm, pl, 0, lane, t);
 		layer2_forward(h, sm, pl, OUT, S, 0, k, lane, g, t);
@@ -378,7 +476,7 @@ __global__ void __launch_bounds__(256, 2) decode_opacity_kernel(DecodeArgs a)
 			if (r < n_vis) {
 				uint32_t bits = 0;
 				for (int j = 0; j < k; j++)
-					if (tanhf(OUT[lane * S + j]) > 0.0f) bits |= 1u << j;
+					if (OUT[lane * S + j] > 0.0f) bits |= 1u << j;   // == tanhf(.) > 0: tanh keeps the sign and does not underflow to 0
 				a.count[r] = (uint32_t)__popc(bits);
 				a.maskbits[r] = bits;
 			}
@@ -388,6 +486,12 @@ __global__ void __launch_bounds__(256, 2) decode_opacity_kernel(DecodeArgs a)
 }
 
 // ---- stage 2: the other three MLPs + post-processing into the compacted outputs ------------------------------------
+struct OutPair {          // one (anchor, offset) pair of the post-processing pass and what it reads from global memory
+	bool keep;
+	int aa, j;
+	size_t p;
+	float off[3], nop;
+};
 __global__ void __launch_bounds__(256, 2) decode_outputs_kernel(DecodeArgs a)
 {
 	extern __shared__ __align__(16) float sm[];
@@ -399,16 +503,45 @@ __global__ void __launch_bounds__(256, 2) decode_outputs_kernel(DecodeArgs a)
 	load_weights(sm, pl, cp, a.wt, k, 1, 4, false, tid);
 	__syncthreads();
 	float *OUT = sm + pl.warp0 + warp * pl.per_warp + pl.out;
+	float *TAB = sm + pl.warp0 + warp * pl.per_warp + pl.tab;
 	const int S = cp.S, cU = cp.cb[1], cC = cp.cb[2], cR = cp.cb[3];
 	const int n_vis = a.n_vis_dev ? (int)*a.n_vis_dev : a.n_vis; // (device copy when the host has not read the counts yet)
 	const int ntiles = (n_vis + kTile - 1) / kTile;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
 	TileRaw raw;
-	fetch_tile(raw, blockIdx.x * kWarps + warp, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+	fetch_tile<true>(raw, blockIdx.x * kWarps + warp, ntiles, n_vis, a, g, t);
 	for (int tile = blockIdx.x * kWarps + warp; tile < ntiles; tile += gridDim.x * kWarps) {
 		TileX x;
 		stage_tile(x, raw, cx, cy, cz, t);
-		fetch_tile(raw, tile + gridDim.x * kWarps, ntiles, n_vis, a.vis_ids, a.anchor, a.feat, g, t);
+		write_table(TAB, raw, g, t);
+		fetch_tile<true>(raw, tile + gridDim.x * kWarps, ntiles, n_vis, a, g, t);
+		__syncwarp();
+		// lanes = (anchor, offset) pairs; the first round's loads are issued here, ahead of the MLPs
+		auto load_out_pair = [&](int idx) {
+			OutPair q;
+			q.keep = false;
+			q.aa = q.j = 0;
+			q.p = 0;
+			q.off[0] = q.off[1] = q.off[2] = q.nop = 0.f;
+			if (idx < kTile * k) {
+				q.aa = idx / k;
+				q.j = idx - q.aa * k;
+				const float *tb = TAB + q.aa * kTab;
+				const uint32_t bits = __float_as_uint(tb[1]);        // 0 for rows past n_vis
+				if ((bits >> q.j) & 1u) {
+					q.keep = true;
+					const int id = __float_as_int(tb[0]);
+					q.p = (size_t)__float_as_uint(tb[2]) + __popc(bits & ((1u << q.j) - 1u));
+					const float *off = a.offset + ((size_t)id * k + q.j) * 3;
+					q.off[0] = __ldg(off);
+					q.off[1] = __ldg(off + 1);
+					q.off[2] = __ldg(off + 2);
+					q.nop = __ldg(a.neural_opacity + (size_t)(tile * kTile + q.aa) * k + q.j);
+				}
+			}
+			return q;
+		};
+		OutPair cur = load_out_pair(lane);
 #pragma unroll
 		for (int m = 1; m < 4; m++) {
 			float h[4][4];
@@ -417,32 +550,29 @@ __global__ void __launch_bounds__(256, 2) decode_outputs_kernel(DecodeArgs a)
 		}
 		__syncwarp();
 		for (int idx = lane; idx < kTile * k; idx += 32) {
-			const int aa = idx / k, j = idx - aa * k;
-			const int r = tile * kTile + aa;
-			if (r >= n_vis) continue;
-			const uint32_t bits = __ldg(a.maskbits + r);
-			if (!((bits >> j) & 1u)) continue;
-			const int id = a.vis_ids ? (int)__ldg(a.vis_ids + r) : r;
-			const size_t p = (size_t)(__ldg(a.gauss_incl + r) - (uint32_t)__popc(bits)) + __popc(bits & ((1u << j) - 1u));
-			const float *gs = a.scaling + (size_t)id * 6;
-			const float *off = a.offset + ((size_t)id * k + j) * 3;
-			const float *an = a.anchor + (size_t)id * 3;
-			const float *row = OUT + aa * S;
-			a.out_opacity[p] = __ldg(a.neural_opacity + (size_t)r * k + j);
-			a.out_uncertainty[p] = sigmoidf_(row[cU + j]);
-			float sr[7];
+			const OutPair nx = load_out_pair(idx + 32);      // the next round's loads fly during this round's arithmetic
+			if (cur.keep) {
+				const float *tb = TAB + cur.aa * kTab, *gs = tb + 6, *an = tb + 3;
+				const float *row = OUT + cur.aa * S;
+				const size_t p = cur.p;
+				const int j = cur.j;
+				a.out_opacity[p] = cur.nop;
+				a.out_uncertainty[p] = sigmoidf_(row[cU + j]);
+				float sr[7];
 #pragma unroll
-			for (int c = 0; c < 7; c++) sr[c] = row[cC + 7 * j + c];
+				for (int c = 0; c < 7; c++) sr[c] = row[cC + 7 * j + c];
 #pragma unroll
-			for (int c = 0; c < 3; c++) {
-				a.out_color[p * 3 + c] = sigmoidf_(row[cR + 3 * j + c]);
-				a.out_scaling[p * 3 + c] = __ldg(gs + 3 + c) * sigmoidf_(sr[c]);                 // :89
-				a.out_xyz[p * 3 + c] = __ldg(an + c) + __ldg(off + c) * __ldg(gs + c);          // :93-94
+				for (int c = 0; c < 3; c++) {
+					a.out_color[p * 3 + c] = sigmoidf_(row[cR + 3 * j + c]);
+					a.out_scaling[p * 3 + c] = gs[3 + c] * sigmoidf_(sr[c]);                         // :89
+					a.out_xyz[p * 3 + c] = an[c] + cur.off[c] * gs[c];                              // :93-94
+				}
+				// F.normalize (scene/gaussian_model.py:52): v / max(||v||, 1e-12)
+				const float nrm = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
+#pragma unroll
+				for (int c = 0; c < 4; c++) a.out_rot[p * 4 + c] = sr[3 + c] / nrm;
 			}
-			// F.normalize (scene/gaussian_model.py:52): v / max(||v||, 1e-12)
-			const float nrm = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
-#pragma unroll
-			for (int c = 0; c < 4; c++) a.out_rot[p * 4 + c] = sr[3 + c] / nrm;
+			cur = nx;
 		}
 		__syncwarp();
 	}
@@ -453,6 +583,11 @@ __global__ void __launch_bounds__(256, 2) decode_outputs_kernel(DecodeArgs a)
 // kept Gaussians into gradients of the 12k output pre-activations (in place over OUT), back-propagate through layer 2 and
 // layer 1 in registers, write d_feat / d_anchor / d_offset / d_scaling.  After a CTA barrier all eight warps run part B over
 // the iteration's X / OUT tiles (see the file header).  KMT = 16-row tiles of the widest MLP (cov: 7k rows).
+struct BwdPair {          // one (anchor, offset) pair of the activation-backward pass and what it reads from global memory
+	bool on, valid, keep;
+	int aa, j, aid;
+	float g_nop, g_opa, g_unc, g_col[3], g_scl[3], g_xyz[3], g_rot[4], off[3];
+};
 template <int KMT>
 __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a, int tiles)
 {
@@ -469,6 +604,7 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 	float *OUT = sm + pl.warp0 + my * pl.per_warp + pl.out;
 	float *X = sm + pl.warp0 + my * pl.per_warp + pl.x;
 	float *PP = sm + pl.warp0 + my * pl.per_warp + pl.pp;
+	float *TAB = sm + pl.warp0 + my * pl.per_warp + pl.tab;
 	const int n_vis = a.f.n_vis;
 	const int ntiles = (n_vis + kTile - 1) / kTile;
 	const int cta_iters = (ntiles + gridDim.x * tiles - 1) / (gridDim.x * tiles);
@@ -490,7 +626,7 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 	const float b1lo = sm[pl.b1 + mB * kHid + 16 * hh + g], b1hi = sm[pl.b1 + mB * kHid + 16 * hh + g + 8];
 
 	TileRaw raw;
-	fetch_tile(raw, warp < tiles ? blockIdx.x * tiles + warp : ntiles, ntiles, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, g, t);
+	fetch_tile<true>(raw, warp < tiles ? blockIdx.x * tiles + warp : ntiles, ntiles, n_vis, a.f, g, t);
 	for (int it = 0; it < cta_iters; it++) {
 		const int first = (it * gridDim.x + blockIdx.x) * tiles;     // this iteration's tiles: first .. first + tiles - 1
 		const int tile = first + warp;
@@ -512,7 +648,56 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 				xr[32 + t] = x.xa[4][q];
 				if (t == 0) xr[40] = __int_as_float(raw.valid[q] ? raw.id[q] : -1);
 			}
-			fetch_tile(raw, tile + gridDim.x * tiles, ntiles, n_vis, a.f.vis_ids, a.f.anchor, a.f.feat, g, t);
+			write_table(TAB, raw, g, t);
+			fetch_tile<true>(raw, tile + gridDim.x * tiles, ntiles, n_vis, a.f, g, t);
+			__syncwarp();
+			// lanes = (anchor, offset) pairs of the activation-backward pass; the loader only ISSUES loads (no arithmetic on the
+			// loaded values), and the first round's go out here, ahead of the recomputation
+			auto load_bwd_pair = [&](int idx) {
+				BwdPair q;
+				q.on = idx < kTile * k;
+				q.valid = q.keep = false;
+				q.aa = q.j = q.aid = 0;
+				q.g_nop = q.g_opa = q.g_unc = 0.f;
+#pragma unroll
+				for (int c = 0; c < 3; c++) q.g_col[c] = q.g_scl[c] = q.g_xyz[c] = q.off[c] = 0.f;
+#pragma unroll
+				for (int c = 0; c < 4; c++) q.g_rot[c] = 0.f;
+				if (q.on) {
+					q.aa = idx / k;
+					q.j = idx - q.aa * k;
+					const int r = tile * kTile + q.aa;
+					q.valid = r < n_vis;
+					if (q.valid) {
+						const float *tb = TAB + q.aa * kTab;
+						const uint32_t bits = __float_as_uint(tb[1]);
+						q.keep = (bits >> q.j) & 1u;
+						q.aid = __float_as_int(tb[0]);
+						if (a.d_neural_opacity) q.g_nop = __ldg(a.d_neural_opacity + (size_t)r * k + q.j);
+						if (q.keep) {
+							const size_t p = (size_t)__float_as_uint(tb[2]) + __popc(bits & ((1u << q.j) - 1u));
+							const float *off = a.f.offset + ((size_t)q.aid * k + q.j) * 3;
+							if (a.d_opacity) q.g_opa = __ldg(a.d_opacity + p);
+							if (a.d_uncertainty) q.g_unc = __ldg(a.d_uncertainty + p);
+#pragma unroll
+							for (int c = 0; c < 3; c++) {
+								if (a.d_color) q.g_col[c] = __ldg(a.d_color + p * 3 + c);
+								if (a.d_scaling) q.g_scl[c] = __ldg(a.d_scaling + p * 3 + c);
+								if (a.d_xyz) {
+									q.g_xyz[c] = __ldg(a.d_xyz + p * 3 + c);
+									q.off[c] = __ldg(off + c);
+								}
+							}
+							if (a.d_rot) {
+#pragma unroll
+								for (int c = 0; c < 4; c++) q.g_rot[c] = __ldg(a.d_rot + p * 4 + c);
+							}
+						}
+					}
+				}
+				return q;
+			};
+			BwdPair cur = load_bwd_pair(lane);
 			uint32_t relu[2] = {0u, 0u};        // bit (16 (m & 1) + 4 nt + e) of relu[m >> 1]: H[m] fragment element > 0
 #pragma unroll
 			for (int m = 0; m < 4; m++) {
@@ -529,29 +714,20 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 
 			// ---- output activations backward; lanes = (anchor, offset) pairs ----------------------------------------
 			for (int idx0 = 0; idx0 < kTile * k; idx0 += 32) {
-				const int idx = idx0 + lane;
-				const bool on = idx < kTile * k;
-				const int aa = on ? idx / k : 0, j = on ? idx - aa * k : 0;
-				const int r = tile * kTile + aa;
-				const bool valid = on && r < n_vis;
-				float *row = OUT + aa * S;
+				const BwdPair nx = load_bwd_pair(idx0 + 32 + lane);   // the next round's loads fly during this round's arithmetic
+				const int j = cur.j;
+				float *row = OUT + cur.aa * S;
 				float d_op = 0.f, d_unc = 0.f, d_col[3] = {0.f, 0.f, 0.f}, d_sr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 				float pp[kPP] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-				if (valid) {
-					const uint32_t bits = __ldg(a.f.maskbits + r);
-					const bool keep = (bits >> j) & 1u;
-					const int aid = a.f.vis_ids ? (int)__ldg(a.f.vis_ids + r) : r;
+				if (cur.valid) {
+					const float *gs = TAB + cur.aa * kTab + 6;
 					const float nop = tanhf(row[j]);
-					float g_op = a.d_neural_opacity ? __ldg(a.d_neural_opacity + (size_t)r * k + j) : 0.f;
-					float dxyz[3] = {0.f, 0.f, 0.f};
-					if (keep) {
-						const size_t p = (size_t)(__ldg(a.f.gauss_incl + r) - (uint32_t)__popc(bits)) + __popc(bits & ((1u << j) - 1u));
-						const float *gs = a.f.scaling + (size_t)aid * 6;
-						const float *off = a.f.offset + ((size_t)aid * k + j) * 3;
-						if (a.d_opacity) g_op += __ldg(a.d_opacity + p);
+					float g_op = cur.g_nop;
+					if (cur.keep) {
+						g_op += cur.g_opa;
 						if (a.d_uncertainty) {
 							const float s = sigmoidf_(row[cU + j]);
-							d_unc = __ldg(a.d_uncertainty + p) * s * (1.f - s);
+							d_unc = cur.g_unc * s * (1.f - s);
 						}
 						float sr[7];
 #pragma unroll
@@ -560,47 +736,43 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 						for (int c = 0; c < 3; c++) {
 							if (a.d_color) {
 								const float s = sigmoidf_(row[cR + 3 * j + c]);
-								d_col[c] = __ldg(a.d_color + p * 3 + c) * s * (1.f - s);
+								d_col[c] = cur.g_col[c] * s * (1.f - s);
 							}
 							if (a.d_scaling) {
 								const float s = sigmoidf_(sr[c]);
-								const float gsc = __ldg(a.d_scaling + p * 3 + c);
-								d_sr[c] = gsc * __ldg(gs + 3 + c) * s * (1.f - s);
+								const float gsc = cur.g_scl[c];
+								d_sr[c] = gsc * gs[3 + c] * s * (1.f - s);
 								pp[6 + c] = gsc * s;                      // d get_scaling[:, 3 + c]
 							}
 							if (a.d_xyz) {
-								dxyz[c] = __ldg(a.d_xyz + p * 3 + c);
-								pp[c] = dxyz[c];                          // d anchor
-								pp[3 + c] = dxyz[c] * __ldg(off + c);     // d get_scaling[:, c]
+								pp[c] = cur.g_xyz[c];                     // d anchor
+								pp[3 + c] = cur.g_xyz[c] * cur.off[c];    // d get_scaling[:, c]
 							}
 						}
 						if (a.d_rot) {
 							// r = v / max(|v|, eps):  dv = (g - r (r . g)) / max(|v|, eps)   (|v| > eps branch; below it dv = g / eps)
 							const float n2 = sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6];
 							const float nrm = sqrtf(n2);
-							float gr[4], dot = 0.f;
+							float dot = 0.f;
 #pragma unroll
-							for (int c = 0; c < 4; c++) {
-								gr[c] = __ldg(a.d_rot + p * 4 + c);
-								dot += gr[c] * sr[3 + c];
-							}
+							for (int c = 0; c < 4; c++) dot += cur.g_rot[c] * sr[3 + c];
 							if (nrm > 1e-12f) {
 #pragma unroll
-								for (int c = 0; c < 4; c++) d_sr[3 + c] = (gr[c] - sr[3 + c] * dot / n2) / nrm;
+								for (int c = 0; c < 4; c++) d_sr[3 + c] = (cur.g_rot[c] - sr[3 + c] * dot / n2) / nrm;
 							} else {
 #pragma unroll
-								for (int c = 0; c < 4; c++) d_sr[3 + c] = gr[c] / 1e-12f;
+								for (int c = 0; c < 4; c++) d_sr[3 + c] = cur.g_rot[c] / 1e-12f;
 							}
 						}
 						if (a.d_xyz) {
 #pragma unroll
-							for (int c = 0; c < 3; c++) a.g_offset[((size_t)aid * k + j) * 3 + c] = dxyz[c] * __ldg(gs + c);
+							for (int c = 0; c < 3; c++) a.g_offset[((size_t)cur.aid * k + j) * 3 + c] = cur.g_xyz[c] * gs[c];
 						}
 					}
 					d_op = g_op * (1.f - nop * nop);
 				}
 				__syncwarp();
-				if (on) {
+				if (cur.on) {
 					// gradients of the pre-activations replace the pre-activations (all reads of this pair's slots are done)
 					row[j] = d_op;
 					row[cU + j] = d_unc;
@@ -609,15 +781,19 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 #pragma unroll
 					for (int c = 0; c < 3; c++) row[cR + 3 * j + c] = d_col[c];
 #pragma unroll
-					for (int c = 0; c < kPP; c++) PP[idx * kPP + c] = pp[c];
+					for (int c = 0; c < kPP; c++) PP[(idx0 + lane) * kPP + c] = pp[c];
 				}
+				cur = nx;
 			}
 			__syncwarp();
 
 			// ---- layer 2 backward (gated by the relu of layer 1), layer 1 backward: registers ----------------------------
-			float dx[5][4];
+			float dx[5][4], dxc[5][4];
 #pragma unroll
-			for (int nt = 0; nt < 5; nt++) dx[nt][0] = dx[nt][1] = dx[nt][2] = dx[nt][3] = 0.f;
+			for (int nt = 0; nt < 5; nt++) {
+				zero4(dx[nt]);
+				zero4(dxc[nt]);
+			}
 #pragma unroll
 			for (int m = 0; m < 4; m++) {
 				float dh[4][4];
@@ -627,8 +803,10 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 #pragma unroll
 					for (int e = 0; e < 4; e++)
 						if (!((relu[m >> 1] >> (16 * (m & 1) + 4 * nt + e)) & 1u)) dh[nt][e] = 0.f;
-				layer1_backward(dx, dh, sm, pl, m, lane);
+				layer1_backward(dx, dxc, dh, sm, pl, m, lane);
 			}
+#pragma unroll
+			for (int nt = 0; nt < 5; nt++) add4(dx[nt], dxc[nt]);
 			// d feat: lane t holds features 8t .. 8t+7 of rows g (c0, c1) and g+8 (c2, c3)
 			if (v0) {
 				float4 *o = reinterpret_cast<float4 *>(a.g_feat + (size_t)id0 * kHid + 8 * t);
@@ -675,52 +853,68 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 
 		// ==================================================== part B ====================================================
 		const int live = min(tiles, ntiles - first);              // tiles of this iteration that exist (<= 0: none)
-		for (int q = 0; q < 2 * live; q++) {
-			const float *Xt = sm + pl.warp0 + (q >> 1) * pl.per_warp + pl.x + (q & 1) * 8 * kSX;
-			const float *Dt = sm + pl.warp0 + (q >> 1) * pl.per_warp + pl.out + (q & 1) * 8 * S;
-			// H^T = relu(W1 x^T + b1): rows h = 16hh + g (+8), columns = anchors 2t (+1) of this n-tile
-			float hT[4] = {b1lo, b1lo, b1hi, b1hi};
+		for (int w = 0; w < live; w++) {
+			// both 8-anchor halves of tile w at once: independent chains for the tensor pipe
+			const float *Xt = sm + pl.warp0 + w * pl.per_warp + pl.x;
+			const float *Dt = sm + pl.warp0 + w * pl.per_warp + pl.out;
+			// H^T = relu(W1 x^T + b1): rows h = 16hh + g (+8), columns = anchors 2t (+1) of the n-tile
+			float hT[2][4] = {{b1lo, b1lo, b1hi, b1hi}, {b1lo, b1lo, b1hi, b1hi}}, hC[2][4];
+			zero4(hC[0]);
+			zero4(hC[1]);
 #pragma unroll
 			for (int ks = 0; ks < 5; ks++) {
 				const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w1f + (((mB * 5 + ks) * 2 + hh) * 32 + lane) * 4);
 				const AFrag wa = make_a(e.x, e.z, e.y, e.w);
-				const float *xr = Xt + g * kSX;
-				const float xb0 = ks < 4 ? xr[8 * t + ks] : xr[32 + t];
-				const float xb1 = ks < 4 ? xr[8 * t + 4 + ks] : 0.f;
-				mma3(hT, wa, xb0, xb1);
+#pragma unroll
+				for (int sub = 0; sub < 2; sub++) {
+					const float *xr = Xt + (8 * sub + g) * kSX;
+					const float xb0 = ks < 4 ? xr[8 * t + ks] : xr[32 + t];
+					const float xb1 = ks < 4 ? xr[8 * t + 4 + ks] : 0.f;
+					mma3(hT[sub], hC[sub], wa, xb0, xb1);
+				}
 			}
 			// dH^T = W2^T dOUT^T, gated
-			float dT[4] = {0.f, 0.f, 0.f, 0.f};
+			float dT[2][4], dC[2][4];
+			zero4(dT[0]); zero4(dT[1]); zero4(dC[0]); zero4(dC[1]);
 			for (int ks = 0; ks < nksB; ks++) {
 				const float4 e = *reinterpret_cast<const float4 *>(sm + pl.w2b + (((cbB >> 3) + ks) * 2 + hh) * 128 + lane * 4);
 				const AFrag wa = make_a(e.x, e.z, e.y, e.w);
-				const float *dr = Dt + g * S + cbB + 8 * ks + t;
-				mma3(dT, wa, dr[0], dr[4]);
+#pragma unroll
+				for (int sub = 0; sub < 2; sub++) {
+					const float *dr = Dt + (8 * sub + g) * S + cbB + 8 * ks + t;
+					mma3(dT[sub], dC[sub], wa, dr[0], dr[4]);
+				}
 			}
 #pragma unroll
-			for (int e = 0; e < 4; e++) {
-				if (!(hT[e] > 0.f)) dT[e] = 0.f;
-				hT[e] = fmaxf(hT[e], 0.f);
+			for (int sub = 0; sub < 2; sub++) {
+#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const float hv = hT[sub][e] + hC[sub][e];
+					dT[sub][e] = hv > 0.f ? dT[sub][e] + dC[sub][e] : 0.f;
+					hT[sub][e] = fmaxf(hv, 0.f);
+				}
+				accb1[0] += dT[sub][0] + dT[sub][1];
+				accb1[1] += dT[sub][2] + dT[sub][3];
 			}
-			accb1[0] += dT[0] + dT[1];
-			accb1[1] += dT[2] + dT[3];
 			// dW1 += dH^T x   (A = the dT fragment, contraction = the 8 anchors; B from the X tile)
-			{
-				const AFrag da = c_as_a(dT);
-				const float *x0 = Xt + (2 * t) * kSX + g, *x1 = x0 + kSX;
+#pragma unroll
+			for (int sub = 0; sub < 2; sub++) {
+				const AFrag da = c_as_a(dT[sub]);
+				const float *x0 = Xt + (8 * sub + 2 * t) * kSX + g, *x1 = x0 + kSX;
 #pragma unroll
 				for (int nt = 0; nt < 5; nt++) mma3(acc1[nt], da, x0[8 * nt], x1[8 * nt]);
 			}
 			// dW2 += dOUT^T H   (A from the dOUT tile: rows o = 16mt + g (+8), contraction = anchors; B = the hT fragment)
-			{
-				const float *d0 = Dt + (2 * t) * S + cbB + g, *d1 = d0 + S;
+#pragma unroll
+			for (int sub = 0; sub < 2; sub++) {
+				const float *d0 = Dt + (8 * sub + 2 * t) * S + cbB + g, *d1 = d0 + S;
 #pragma unroll
 				for (int mt = 0; mt < KMT; mt++) {
 					if (mt < nmtB) {
 						const float a0 = d0[16 * mt], a1 = d0[16 * mt + 8], a2 = d1[16 * mt], a3 = d1[16 * mt + 8];
 						const AFrag oa = make_a(a0, a1, a2, a3);
-						mma3(acc2[mt][0], oa, hT[0], hT[1]);
-						mma3(acc2[mt][1], oa, hT[2], hT[3]);
+						mma3(acc2[mt][0], oa, hT[sub][0], hT[sub][1]);
+						mma3(acc2[mt][1], oa, hT[sub][2], hT[sub][3]);
 						accb2[mt][0] += a0 + a2;
 						accb2[mt][1] += a1 + a3;
 					}
@@ -848,6 +1042,14 @@ cudaError_t set_smem(K kernel, size_t bytes)
 {
 	return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+// resident CTAs per SM of a persistent forward kernel with this much shared memory (2 at k <= 10, 1 above)
+template <typename K>
+int resident_ctas(K kernel, size_t smem)
+{
+	int n = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, smem) != cudaSuccess || n < 1) n = 1;
+	return min(n, GSR_DEC_FWD_CTAS);
+}
 
 } // namespace
 
@@ -888,7 +1090,7 @@ cudaError_t decode_stage1(int A, int k, const float *anchor, const float *feat, 
 	a.neural_opacity = neural_opacity; a.mask = mask; a.count = count; a.maskbits = bits;
 	const size_t smem = (size_t)smem_plan(k, 0, 1, false, kWarps).total * 4;
 	if ((e = set_smem(decode_opacity_kernel, smem)) != cudaSuccess) return e;
-	decode_opacity_kernel<<<grid_for(A, GSR_DEC_FWD_CTAS, kWarps), 256, smem, stream>>>(a);
+	decode_opacity_kernel<<<grid_for(A, resident_ctas(decode_opacity_kernel, smem), kWarps), 256, smem, stream>>>(a);
 	count_launch(2);
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if ((e = inclusive_sum_gather(count, nullptr, gincl, A, scratch + L.scan_tmp, stream)) != cudaSuccess) return e;
@@ -904,7 +1106,7 @@ cudaError_t decode_stage2(const DecodeArgs &a, cudaStream_t stream)
 	cudaError_t e;
 	const size_t smem = (size_t)smem_plan(a.k, 1, 4, false, kWarps).total * 4;
 	if ((e = set_smem(decode_outputs_kernel, smem)) != cudaSuccess) return e;
-	decode_outputs_kernel<<<grid_for(a.n_vis, GSR_DEC_FWD_CTAS, kWarps), 256, smem, stream>>>(a);
+	decode_outputs_kernel<<<grid_for(a.n_vis, resident_ctas(decode_outputs_kernel, smem), kWarps), 256, smem, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }
