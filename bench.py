@@ -602,7 +602,7 @@ def run_train_step(args, rank, world, local):
                                   "achieved_fwd": fwd_bytes / (st["decode_forward"] * 1e-3) / 1e9 if st["decode_forward"] else None,
                                   "achieved_bwd": bwd_bytes / (st["decode_backward"] * 1e-3) / 1e9 if st["decode_backward"] else None,
                                   "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-                                  "note": "8.4 kMAC of MLP per anchor against ~0.7 KB: FP32-FMA / shared-memory bound, not HBM bound"}}
+                                  "note": "8.4 kMAC of MLP per anchor against ~0.7 KB: not HBM bound; 3xTF32 mma.sync on the tensor pipe, bounded by warps in flight (profiles/r2_decode_mma.md)"}}
     out["gpu_launches"] = launches
     return out
 

@@ -144,7 +144,9 @@ def _compare_with_restatement(A, k, seed, vis_frac, dev, bias_shift=None):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("A,k,seed,vis_frac", [(20000, 10, 21, 0.7), (4099, 10, 22, None), (1, 10, 23, None), (5, 16, 24, 0.9),
-                                                (37, 1, 25, None), (1000, 4, 26, 0.05)])
+                                                (37, 1, 25, None), (1000, 4, 26, 0.05),
+                                                # k > 10: four tiles per CTA iteration and the 7-row-tile instantiation of the backward
+                                                (3001, 16, 27, 0.8), (2050, 11, 28, None)])
 def test_gpu_decode_matches_fp64_restatement(A, k, seed, vis_frac):
     P = _compare_with_restatement(A, k, seed, vis_frac, torch.device("cuda"))
     assert P >= 0
