@@ -1,7 +1,8 @@
 """Scratch: tiny runs of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
 rasterizer fwd+bwd (C = 32 ragged, C = 3, long tile lists, packed and plain point lists), fused decode fwd+bwd, fused L1+SSIM
 fwd+bwd, densification statistics; aligned-depth L1 + four-scale gradient loss fwd+bwd and the multi-tensor Adam step
-(`python tests/_sanitize.py new` runs only that last group)."""
+(`python tests/_sanitize.py new` runs only that last group; `python tests/_sanitize.py decode` only the decode kernels, forward and
+backward, on inputs spanning several tiles per warp and several CTA iterations at k = 10, 16 and 3)."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,6 +10,19 @@ import _ref_utils as ru
 import _anchor_decode as ad
 from gscream_b200 import _lib, decode, losses, scenes, stats, rasterizer as ours
 lib = _lib.load()
+if len(sys.argv) > 1 and sys.argv[1] == "decode":
+    dev = torch.device("cuda")
+    class _C:
+        camera_center = torch.tensor([0.05, 0.1, -0.3], device=dev)
+    # 148 CTAs x 8 tiles x 16 anchors = 18 944 anchors per CTA iteration at k <= 10 (half of that above): the first case needs two
+    for (A, k, frac) in ((24000, 10, 0.9), (10500, 16, None), (333, 3, 0.5)):
+        pc = ad.SyntheticAnchors(A, n_offsets=k, seed=A).to(dev)
+        vis = None if frac is None else (torch.rand(A, device=dev) < frac)
+        outs = decode.generate_neural_gaussians(_C, pc, vis, is_training=True)
+        sum((o * torch.randn_like(o)).sum() for o in outs[:7]).backward()
+        torch.cuda.synchronize()
+        print("decode ok", A, k, outs[0].shape[0])
+    sys.exit(0)
 ONLY_NEW = len(sys.argv) > 1 and sys.argv[1] == "new"
 for plain in (() if ONLY_NEW else (0, 1)):
     lib.gsr_debug_plain_point_list(plain)
