@@ -698,17 +698,22 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 				return q;
 			};
 			BwdPair cur = load_bwd_pair(lane);
-			uint32_t relu[2] = {0u, 0u};        // bit (16 (m & 1) + 4 nt + e) of relu[m >> 1]: H[m] fragment element > 0
-#pragma unroll
+			// (the loops over the four MLPs stay rolled: unrolled, the kernel is 9.6 k instructions and its eight warps, spread
+			// over part A and part B code, miss the instruction cache)
+			unsigned long long relu = 0ull;     // bit (16 m + 4 nt + e): H[m] fragment element > 0
+#pragma unroll 1
 			for (int m = 0; m < 4; m++) {
+				const int cbm = m == 0 ? 0 : m == 1 ? cU : m == 2 ? cC : cR;
 				float h[4][4];
 				layer1_forward(h, x, sm, pl, m, lane, t);
+				uint32_t bits = 0u;
 #pragma unroll
 				for (int nt = 0; nt < 4; nt++)
 #pragma unroll
 					for (int e = 0; e < 4; e++)
-						if (h[nt][e] > 0.f) relu[m >> 1] |= 1u << (16 * (m & 1) + 4 * nt + e);
-				layer2_forward(h, sm, pl, OUT, S, cp.cb[m], out_count(m, k), lane, g, t);
+						if (h[nt][e] > 0.f) bits |= 1u << (4 * nt + e);
+				relu |= (unsigned long long)bits << (16 * m);
+				layer2_forward(h, sm, pl, OUT, S, cbm, out_count(m, k), lane, g, t);
 			}
 			__syncwarp();
 
@@ -794,15 +799,17 @@ __global__ void __launch_bounds__(256, 1) decode_backward_kernel(DecodeBwdArgs a
 				zero4(dx[nt]);
 				zero4(dxc[nt]);
 			}
-#pragma unroll
+#pragma unroll 1
 			for (int m = 0; m < 4; m++) {
+				const int cbm = m == 0 ? 0 : m == 1 ? cU : m == 2 ? cC : cR;
 				float dh[4][4];
-				layer2_backward(dh, sm, pl, OUT, S, cp.cb[m], out_count(m, k), lane, g, t);
+				layer2_backward(dh, sm, pl, OUT, S, cbm, out_count(m, k), lane, g, t);
+				const uint32_t bits = (uint32_t)(relu >> (16 * m));
 #pragma unroll
 				for (int nt = 0; nt < 4; nt++)
 #pragma unroll
 					for (int e = 0; e < 4; e++)
-						if (!((relu[m >> 1] >> (16 * (m & 1) + 4 * nt + e)) & 1u)) dh[nt][e] = 0.f;
+						if (!((bits >> (4 * nt + e)) & 1u)) dh[nt][e] = 0.f;
 				layer1_backward(dx, dxc, dh, sm, pl, m, lane);
 			}
 #pragma unroll
