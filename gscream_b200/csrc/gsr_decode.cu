@@ -449,6 +449,8 @@ __global__ void __launch_bounds__(256, 2) decode_opacity_kernel(DecodeArgs a)
 	const int S = cp.S;
 	const int n_vis = a.n_vis_dev ? (int)*a.n_vis_dev : a.n_vis;
 	const int ntiles = (n_vis + kTile - 1) / kTile;
+	// the scan behind this kernel runs over all A counts: ranks past the visible anchors count nothing
+	for (int r = n_vis + blockIdx.x * 256 + tid; r < a.n_vis; r += gridDim.x * 256) a.count[r] = 0u;
 	const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
 	TileRaw raw;
 	fetch_tile<false>(raw, blockIdx.x * kWarps + warp, ntiles, n_vis, a, g, t);
@@ -1007,18 +1009,6 @@ __global__ void __launch_bounds__(256) training_statis_kernel(int A, int k, int6
 	anchor_demon[a] += 1.f;
 }
 
-// ---- small helpers for the visible-anchor list ------------------------------------------------------------------------
-__global__ void mask_to_flags_kernel(int A, const uint8_t *__restrict__ mask, uint32_t *__restrict__ flags)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < A) flags[i] = mask[i] ? 1u : 0u;
-}
-__global__ void compact_visible_kernel(int A, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ incl, uint32_t *__restrict__ ids)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < A && flags[i]) ids[incl[i] - 1] = (uint32_t)i;
-}
-
 // persistent CTAs per SM of the two forward kernels (<= 100 KB of shared memory and <= 128 registers each)
 #ifndef GSR_DEC_FWD_CTAS
 #define GSR_DEC_FWD_CTAS 2
@@ -1081,15 +1071,11 @@ cudaError_t decode_stage1(int A, int k, const float *anchor, const float *feat, 
                           int64_t *counts_host, cudaStream_t stream)
 {
 	cudaError_t e;
-	uint32_t *flags = (uint32_t *)(scratch + L.vis_flag), *incl = (uint32_t *)(scratch + L.vis_incl), *ids = (uint32_t *)(scratch + L.vis_ids);
+	uint32_t *incl = (uint32_t *)(scratch + L.vis_incl), *ids = (uint32_t *)(scratch + L.vis_ids);
 	uint32_t *count = (uint32_t *)(scratch + L.count), *bits = (uint32_t *)(scratch + L.maskbits), *gincl = (uint32_t *)(scratch + L.gauss_incl);
-	if (visible_mask) {
-		mask_to_flags_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, visible_mask, flags);
-		if ((e = inclusive_sum_gather(flags, nullptr, incl, A, scratch + L.scan_tmp, stream)) != cudaSuccess) return e;
-		compact_visible_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, flags, incl, ids);
-		count_launch(2);
+	if (visible_mask) {   // visible ranks (inclusive scan of the mask) and the ascending list of visible anchors
+		if ((e = inclusive_sum_mask(visible_mask, incl, ids, A, scratch + L.scan_tmp, stream)) != cudaSuccess) return e;
 	}
-	if ((e = cudaMemsetAsync(count, 0, (size_t)A * 4, stream)) != cudaSuccess) return e;
 	DecodeArgs a{};
 	a.k = k; a.n_vis = A; a.n_vis_dev = visible_mask ? incl + (A - 1) : nullptr;
 	a.vis_ids = visible_mask ? ids : nullptr;
@@ -1098,7 +1084,7 @@ cudaError_t decode_stage1(int A, int k, const float *anchor, const float *feat, 
 	const size_t smem = (size_t)smem_plan(k, 0, 1, false, kWarps).total * 4;
 	if ((e = set_smem(decode_opacity_kernel, smem)) != cudaSuccess) return e;
 	decode_opacity_kernel<<<grid_for(A, resident_ctas(decode_opacity_kernel, smem), kWarps), 256, smem, stream>>>(a);
-	count_launch(2);
+	count_launch();
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if ((e = inclusive_sum_gather(count, nullptr, gincl, A, scratch + L.scan_tmp, stream)) != cudaSuccess) return e;
 	// counts_host[0] = n_vis, [1] = P: 4 bytes each into the low halves of pre-zeroed little-endian int64s
@@ -1149,17 +1135,13 @@ cudaError_t training_statis(int A, int k, int64_t n_vis, int64_t P, const uint8_
                             float *offset_gradient_accum, float *offset_denom, char *scratch, cudaStream_t stream)
 {
 	const size_t a = (size_t)A, n = (size_t)n_vis * k;
-	uint32_t *vflag = (uint32_t *)scratch, *vincl = (uint32_t *)(scratch + align_up(a * 4));
-	uint32_t *sflag = (uint32_t *)(scratch + 2 * align_up(a * 4)), *sincl = (uint32_t *)(scratch + 2 * align_up(a * 4) + align_up((size_t)A * k * 4));
+	uint32_t *vincl = (uint32_t *)(scratch + align_up(a * 4));
+	uint32_t *sincl = (uint32_t *)(scratch + 2 * align_up(a * 4) + align_up((size_t)A * k * 4));
 	char *tmp = scratch + 2 * align_up(a * 4) + 2 * align_up((size_t)A * k * 4);
 	cudaError_t e;
-	mask_to_flags_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, anchor_visible, vflag);
-	if ((e = inclusive_sum_gather(vflag, nullptr, vincl, A, tmp, stream)) != cudaSuccess) return e;
-	count_launch();
+	if ((e = inclusive_sum_mask(anchor_visible, vincl, nullptr, A, tmp, stream)) != cudaSuccess) return e;
 	if (n > 0) {
-		mask_to_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)n, offset_selected, sflag);
-		if ((e = inclusive_sum_gather(sflag, nullptr, sincl, (int64_t)n, tmp, stream)) != cudaSuccess) return e;
-		count_launch();
+		if ((e = inclusive_sum_mask(offset_selected, sincl, nullptr, (int64_t)n, tmp, stream)) != cudaSuccess) return e;
 	}
 	training_statis_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, k, n_vis, P, anchor_visible, vincl, offset_selected, sincl, update_filter, neural_opacity,
 	                                                          viewspace_grad, opacity_accum, anchor_demon, offset_gradient_accum, offset_denom);

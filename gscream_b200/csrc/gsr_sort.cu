@@ -257,7 +257,7 @@ int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint3
 // ------------------------------------------------------------------------------------------------
 // inclusive sum of in[order[i]]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRsThreads) scan_local_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ order,
+__global__ void __launch_bounds__(kRsThreads) scan_local_kernel(const uint32_t *__restrict__ in, const uint8_t *__restrict__ in8, const uint32_t *__restrict__ order,
                                                                 uint32_t *__restrict__ out, int64_t n, uint32_t *__restrict__ tile_sums)
 {
 	__shared__ uint32_t s_warp[8];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kRsThreads) scan_local_kernel(const uint32_t *
 	for (int i = 0; i < kRsItems; i++) {
 		const int64_t idx = base + i;
 		uint32_t x = 0;
-		if (idx < n) x = order ? __ldg(in + __ldg(order + idx)) : __ldg(in + idx);
+		if (idx < n) x = in8 ? (__ldg(in8 + idx) ? 1u : 0u) : (order ? __ldg(in + __ldg(order + idx)) : __ldg(in + idx));
 		sum += x;
 		v[i] = sum;
 	}
@@ -295,33 +295,58 @@ __global__ void __launch_bounds__(kRsThreads) scan_tiles_kernel(uint32_t *tile_s
 		carry += tot;
 	}
 }
-__global__ void __launch_bounds__(kRsThreads) scan_add_kernel(uint32_t *__restrict__ out, int64_t n, const uint32_t *__restrict__ tile_prefix)
+// Adds the tile's exclusive prefix.  raw: tile_sums still holds the tile TOTALS (at most kRsThreads tiles) and every CTA sums
+// the ones before it itself — one launch less than scanning them first.  mask8 / ids: compaction of the set entries.
+__global__ void __launch_bounds__(kRsThreads) scan_finish_kernel(uint32_t *__restrict__ out, int64_t n, const uint32_t *__restrict__ tile_sums, int raw,
+                                                                 const uint8_t *__restrict__ mask8, uint32_t *__restrict__ ids)
 {
-	const uint32_t add = tile_prefix[blockIdx.x];
-	if (add == 0) return;
+	__shared__ uint32_t s_warp[8];
+	uint32_t add;
+	if (raw)
+		block_exclusive_scan_256((int)threadIdx.x < (int)blockIdx.x ? tile_sums[threadIdx.x] : 0u, s_warp, &add);
+	else
+		add = tile_sums[blockIdx.x];
+	if (add == 0 && !ids) return;
 	const int64_t base = (int64_t)blockIdx.x * kRsTile;
 #pragma unroll 4
 	for (int i = 0; i < kRsItems; i++) {
 		const int64_t idx = base + i * kRsThreads + threadIdx.x;
-		if (idx < n) out[idx] += add;
+		if (idx < n) {
+			const uint32_t o = out[idx] + add;
+			if (add) out[idx] = o;
+			if (ids && __ldg(mask8 + idx)) ids[o - 1] = (uint32_t)idx;
+		}
 	}
 }
 
 size_t scan_scratch_bytes(int64_t n) { return align_up((size_t)std::max<int64_t>(1, (n + kRsTile - 1) / kRsTile) * 4); }
 
-cudaError_t inclusive_sum_gather(const uint32_t *in, const uint32_t *order, uint32_t *out, int64_t n, void *scratch, cudaStream_t stream)
+static cudaError_t inclusive_sum_any(const uint32_t *in, const uint8_t *in8, const uint32_t *order, uint32_t *out, uint32_t *ids, int64_t n, void *scratch,
+                                     cudaStream_t stream)
 {
 	if (n <= 0) return cudaSuccess;
 	const int tiles = (int)((n + kRsTile - 1) / kRsTile);
 	uint32_t *tile_sums = (uint32_t *)scratch;
-	scan_local_kernel<<<tiles, kRsThreads, 0, stream>>>(in, order, out, n, tile_sums);
+	scan_local_kernel<<<tiles, kRsThreads, 0, stream>>>(in, in8, order, out, n, tile_sums);
 	count_launch();
-	if (tiles > 1) {
-		scan_tiles_kernel<<<1, kRsThreads, 0, stream>>>(tile_sums, tiles);
-		scan_add_kernel<<<tiles, kRsThreads, 0, stream>>>(out, n, tile_sums);
-		count_launch(2);
+	if (tiles > 1 || ids) {
+		const int raw = tiles <= kRsThreads ? 1 : 0;
+		if (!raw) {
+			scan_tiles_kernel<<<1, kRsThreads, 0, stream>>>(tile_sums, tiles);
+			count_launch();
+		}
+		scan_finish_kernel<<<tiles, kRsThreads, 0, stream>>>(out, n, tile_sums, raw, in8, ids);
+		count_launch();
 	}
 	return cudaGetLastError();
+}
+cudaError_t inclusive_sum_gather(const uint32_t *in, const uint32_t *order, uint32_t *out, int64_t n, void *scratch, cudaStream_t stream)
+{
+	return inclusive_sum_any(in, nullptr, order, out, nullptr, n, scratch, stream);
+}
+cudaError_t inclusive_sum_mask(const uint8_t *mask, uint32_t *out, uint32_t *ids, int64_t n, void *scratch, cudaStream_t stream)
+{
+	return inclusive_sum_any(nullptr, mask, nullptr, out, ids, n, scratch, stream);
 }
 
 } // namespace gsr

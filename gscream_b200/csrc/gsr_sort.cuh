@@ -53,5 +53,8 @@ __device__ __forceinline__ int64_t device_count(int64_t cap, const uint32_t *n_d
 // Inclusive prefix sum of in[order[i]] (order may be null: in[i]) into out[0..n).  scratch: scan_scratch_bytes(n).
 size_t scan_scratch_bytes(int64_t n);
 cudaError_t inclusive_sum_gather(const uint32_t *in, const uint32_t *order, uint32_t *out, int64_t n, void *scratch, cudaStream_t stream);
+// Inclusive prefix sum of the 0 / 1 flags of a byte mask (mask[i] != 0) into out[0..n); with ids != null also the compaction
+// ids[out[i] - 1] = i of the set entries (ascending).  Same scratch.
+cudaError_t inclusive_sum_mask(const uint8_t *mask, uint32_t *out, uint32_t *ids, int64_t n, void *scratch, cudaStream_t stream);
 
 } // namespace gsr
