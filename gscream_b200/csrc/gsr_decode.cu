@@ -176,15 +176,16 @@ __host__ __device__ inline int in1b(int nt, int c) { return nt < 4 ? 8 * (c >> 1
 template <typename F>
 __device__ __forceinline__ void fill_smem(float *dst, int n, int tid, F value_of)
 {
-	for (int base = tid; base < n; base += 256 * 8) {
-		float v[8];
+	constexpr int kBatch = 8;     // (16 measured no faster)
+	for (int base = tid; base < n; base += 256 * kBatch) {
+		float v[kBatch];
 #pragma unroll
-		for (int u = 0; u < 8; u++) {
+		for (int u = 0; u < kBatch; u++) {
 			const int idx = base + 256 * u;
 			v[u] = idx < n ? value_of(idx) : 0.f;
 		}
 #pragma unroll
-		for (int u = 0; u < 8; u++) {
+		for (int u = 0; u < kBatch; u++) {
 			const int idx = base + 256 * u;
 			if (idx < n) dst[idx] = v[u];
 		}
@@ -435,7 +436,10 @@ __device__ __forceinline__ void layer1_backward(float (&dx)[5][4], float (&dxc)[
 }
 
 // ---- stage 1: opacity MLP, mask, per-anchor counts ---------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) decode_opacity_kernel(DecodeArgs a)
+#ifndef GSR_DEC_S1_CTAS
+#define GSR_DEC_S1_CTAS 2     // (3 CTAs of 80 registers measured the same: 0.133 ms either way)
+#endif
+__global__ void __launch_bounds__(256, GSR_DEC_S1_CTAS) decode_opacity_kernel(DecodeArgs a)
 {
 	extern __shared__ __align__(16) float sm[];
 	const int k = a.k;
@@ -1041,11 +1045,11 @@ cudaError_t set_smem(K kernel, size_t bytes)
 }
 // resident CTAs per SM of a persistent forward kernel with this much shared memory (2 at k <= 10, 1 above)
 template <typename K>
-int resident_ctas(K kernel, size_t smem)
+int resident_ctas(K kernel, size_t smem, int cap)
 {
 	int n = 0;
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, smem) != cudaSuccess || n < 1) n = 1;
-	return min(n, GSR_DEC_FWD_CTAS);
+	return min(n, cap);
 }
 
 } // namespace
@@ -1083,7 +1087,7 @@ cudaError_t decode_stage1(int A, int k, const float *anchor, const float *feat, 
 	a.neural_opacity = neural_opacity; a.mask = mask; a.count = count; a.maskbits = bits;
 	const size_t smem = (size_t)smem_plan(k, 0, 1, false, kWarps).total * 4;
 	if ((e = set_smem(decode_opacity_kernel, smem)) != cudaSuccess) return e;
-	decode_opacity_kernel<<<grid_for(A, resident_ctas(decode_opacity_kernel, smem), kWarps), 256, smem, stream>>>(a);
+	decode_opacity_kernel<<<grid_for(A, resident_ctas(decode_opacity_kernel, smem, GSR_DEC_S1_CTAS), kWarps), 256, smem, stream>>>(a);
 	count_launch();
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if ((e = inclusive_sum_gather(count, nullptr, gincl, A, scratch + L.scan_tmp, stream)) != cudaSuccess) return e;
@@ -1099,7 +1103,7 @@ cudaError_t decode_stage2(const DecodeArgs &a, cudaStream_t stream)
 	cudaError_t e;
 	const size_t smem = (size_t)smem_plan(a.k, 1, 4, false, kWarps).total * 4;
 	if ((e = set_smem(decode_outputs_kernel, smem)) != cudaSuccess) return e;
-	decode_outputs_kernel<<<grid_for(a.n_vis, resident_ctas(decode_outputs_kernel, smem), kWarps), 256, smem, stream>>>(a);
+	decode_outputs_kernel<<<grid_for(a.n_vis, resident_ctas(decode_outputs_kernel, smem, GSR_DEC_FWD_CTAS), kWarps), 256, smem, stream>>>(a);
 	count_launch();
 	return cudaGetLastError();
 }
