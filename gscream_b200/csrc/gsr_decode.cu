@@ -1059,7 +1059,6 @@ DecodeLayout decode_layout(int A)
 	DecodeLayout L{};
 	size_t off = 0;
 	const size_t n = (size_t)(A > 0 ? A : 1) * 4;
-	L.vis_flag = off;   off += align_up(n);
 	L.vis_incl = off;   off += align_up(n);
 	L.vis_ids = off;    off += align_up(n);
 	L.count = off;      off += align_up(n);
@@ -1131,7 +1130,7 @@ cudaError_t decode_backward(const DecodeBwdArgs &a, cudaStream_t stream)
 size_t statis_scratch_bytes(int A, int k)
 {
 	const size_t a = (size_t)(A > 0 ? A : 1), n = a * (size_t)(k > 0 ? k : 1);
-	return 2 * align_up(a * 4) + 2 * align_up(n * 4) + scan_scratch_bytes((int64_t)n);
+	return align_up(a * 4) + align_up(n * 4) + scan_scratch_bytes((int64_t)n);   // the two inclusive scans + the scan's own scratch
 }
 
 cudaError_t training_statis(int A, int k, int64_t n_vis, int64_t P, const uint8_t *anchor_visible, const uint8_t *offset_selected, const uint8_t *update_filter,
@@ -1139,9 +1138,9 @@ cudaError_t training_statis(int A, int k, int64_t n_vis, int64_t P, const uint8_
                             float *offset_gradient_accum, float *offset_denom, char *scratch, cudaStream_t stream)
 {
 	const size_t a = (size_t)A, n = (size_t)n_vis * k;
-	uint32_t *vincl = (uint32_t *)(scratch + align_up(a * 4));
-	uint32_t *sincl = (uint32_t *)(scratch + 2 * align_up(a * 4) + align_up((size_t)A * k * 4));
-	char *tmp = scratch + 2 * align_up(a * 4) + 2 * align_up((size_t)A * k * 4);
+	uint32_t *vincl = (uint32_t *)scratch;
+	uint32_t *sincl = (uint32_t *)(scratch + align_up(a * 4));
+	char *tmp = scratch + align_up(a * 4) + align_up((size_t)A * k * 4);
 	cudaError_t e;
 	if ((e = inclusive_sum_mask(anchor_visible, vincl, nullptr, A, tmp, stream)) != cudaSuccess) return e;
 	if (n > 0) {

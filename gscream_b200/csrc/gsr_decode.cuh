@@ -14,7 +14,7 @@ struct DecodeWeights {
 };
 
 struct DecodeLayout {  // caller-allocated scratch, sized by gsr_decode_scratch_bytes(A)
-	size_t vis_flag, vis_incl, vis_ids, count, maskbits, gauss_incl, scan_tmp, total;
+	size_t vis_incl, vis_ids, count, maskbits, gauss_incl, scan_tmp, total;
 };
 DecodeLayout decode_layout(int A);
 
