@@ -68,6 +68,23 @@ def test_argument_validation_without_device(lib):
     assert lib.gsr_visible_filter(5, None, None, 3, 1.0, None, None, None, None, 64, 64, 0.5, 0.5, 0, None, None) == -1
 
 
+def test_decode_entry_points_validate_before_launching(lib):
+    """gsr_decode_stage1 rejects unsupported shapes, null inputs and misaligned feature rows (they are moved as float4)
+    without touching the device."""
+    counts = (ctypes.c_int64 * 2)()
+    params = (ctypes.c_void_p * 16)(*([0x1000] * 16))
+    fake = 0x10000            # never dereferenced: validation returns first
+    def stage1(feat_dim, k, feat):
+        return lib.gsr_decode_stage1(8, feat_dim, k, fake, feat, None, fake, params, fake, 1 << 20, fake, fake, ctypes.addressof(counts), None)
+    assert lib.gsr_decode_supported(32, 10) == 1 and lib.gsr_decode_supported(32, 17) == 0 and lib.gsr_decode_supported(16, 10) == 0
+    assert stage1(16, 10, fake) == -1 and stage1(32, 0, fake) == -1       # unsupported feat_dim / n_offsets
+    assert stage1(32, 10, None) == -1                                      # null input
+    assert stage1(32, 10, fake + 4) == -1                                  # feature rows not 16-byte aligned
+    assert lib.gsr_decode_stage1(0, 32, 10, None, None, None, None, None, None, 0, None, None, ctypes.addressof(counts), None) == 0
+    assert counts[0] == 0 and counts[1] == 0                               # A == 0: nothing to do, counts zeroed
+    assert lib.gsr_decode_scratch_bytes(1000) < lib.gsr_decode_scratch_bytes(100000)
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from gscream_b200 import _build, _lib
     monkeypatch.setattr(_lib, "_LIB", None)
