@@ -85,6 +85,12 @@ def _ours(pc, campos, vis, dev):
 def _close(got, ref, tol, name, extra=0.0):
     scale = max(float(np.abs(ref).max()), 1e-6) if ref.size else 1.0
     err = float(np.abs(got - ref).max()) if ref.size else 0.0
+    path = os.environ.get("GSR_PARITY_REPORT")     # one JSON line per comparison: the figure behind the assertion
+    if path:
+        import json
+        with open(path, "a") as fh:
+            fh.write(json.dumps(dict(case=os.environ.get("PYTEST_CURRENT_TEST", "").split("::")[-1].split(" ")[0], tensor=name,
+                                     err_over_scale=err / scale, bound=tol, slack_over_scale=extra / scale)) + "\n")
     assert err <= tol * scale + extra, "%s: max err %.3e vs scale %.3e" % (name, err, scale)
 
 
