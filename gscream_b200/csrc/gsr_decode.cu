@@ -1019,15 +1019,10 @@ __global__ void __launch_bounds__(256) training_statis_kernel(int A, int k, int6
 #endif
 constexpr size_t kMaxSmemBytes = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
-int sm_count()
+int sm_count()   // of the CURRENT device (asked per call: a process may drive several devices)
 {
-	static int sms = 0;
-	if (!sms) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if (sms <= 0) sms = 148;
-	}
+	int dev = 0, sms = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
 	return sms;
 }
 // persistent grid: enough CTAs to cover the tiles (`tiles` per CTA iteration), at most `per_sm` per SM
